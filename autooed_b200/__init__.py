@@ -1,0 +1,13 @@
+"""autooed_b200 — B200-native (sm_100a) GP-surrogate hot path of AutoOED behind the autooed.mobo interfaces.
+
+    from autooed_b200 import GaussianProcess, ExpectedImprovement, HypervolumeImprovement
+
+All numerics run in libaoed_b200.so (hand-written CUDA, C ABI in include/aoed_b200.h); there is no CPU fallback.
+"""
+from autooed_b200.surrogate_model import GaussianProcess
+from autooed_b200.acquisition import Identity, UpperConfidenceBound, ExpectedImprovement, ProbabilityOfImprovement
+from autooed_b200.selection import HypervolumeImprovement
+from autooed_b200.factory import (get_surrogate_model, get_acquisition, get_selection, init_surrogate_model,
+                                  init_acquisition, init_selection)
+
+__version__ = "0.1.0"

@@ -1,0 +1,169 @@
+// Kernels of the hyper-parameter fit (sm_100a, FP64): kernel matrix, LML gradient contraction, small helpers.
+//
+//   kmat_kernel       K = c1 * phi(r) + c2 (+ 1e-10 on the diagonal)      (gp.py:24-58 via sklearn kernel algebra,
+//                     _gpr.py:582-589)
+//   lml_grad_kernel   grad_theta = 1/2 sum_ij (alpha_i alpha_j - Kinv_ij) dK_ij/dtheta, fused: the (N,N,p) tensor of
+//                     gp.py:63-79 / _gpr.py:627-650 is never materialised.
+#pragma once
+#include "common.cuh"
+
+namespace aoed {
+
+struct KmatArgs {
+    const double* Ts;     // [B][Npad][DP] training points / length scale
+    const double* c1c2;   // [B][2]
+    double* K;            // [B][Npad][Npad], full symmetric, zero outside N
+    int N, Npad, DP;
+};
+
+template <int NU, int DP>
+__global__ void __launch_bounds__(256) kmat_kernel(KmatArgs p) {
+    __shared__ __align__(16) double ti[16][DP];
+    __shared__ __align__(16) double tj[16][DP];
+    const int b = blockIdx.z;
+    const int i0 = blockIdx.y * 16, j0 = blockIdx.x * 16;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const double* __restrict__ Ts = p.Ts + int64_t(b) * p.Npad * DP;
+    for (int e = threadIdx.x; e < 16 * DP; e += 256) {
+        int r = e / DP, k = e % DP;
+        ti[r][k] = (i0 + r < p.N) ? Ts[int64_t(i0 + r) * DP + k] : 0.0;
+        tj[r][k] = (j0 + r < p.N) ? Ts[int64_t(j0 + r) * DP + k] : 0.0;
+    }
+    __syncthreads();
+    const int i = i0 + ty, j = j0 + tx;
+    if (i >= p.N || j >= p.N) return;
+    double r2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+        double d = ti[ty][k] - tj[tx][k];
+        r2 = fma(d, d, r2);
+    }
+    double phi, gor;
+    kernel_profile<NU>(sqrt(r2), r2, phi, gor);
+    const double c1 = p.c1c2[2 * b], c2 = p.c1c2[2 * b + 1];
+    double v = fma(c1, phi, c2);
+    if (i == j) v = (c1 + c2) + kJitter;  // np.fill_diagonal(K, 1) (gp.py:55) then K[diag] += alpha (_gpr.py:589)
+    p.K[(int64_t(b) * p.Npad + i) * p.Npad + j] = v;
+}
+
+// dphi/dlog l_k = h(r) * D_k, D_k = ((x_ik - x_jk)/l_k)^2   (gp.py:63-79; RBF: sklearn K * D_k)
+template <int NU>
+__device__ __forceinline__ double h_profile(double r, double r2, double phi) {
+    if (NU == 1) return r != 0.0 ? phi / r : 0.0;  // safe_divide + isfinite guard (gp.py:68-70)
+    if (NU == 3) return 3.0 * exp(-kSqrt3 * r);
+    if (NU == 5) {
+        double s = kSqrt5 * r;
+        return 5.0 / 3.0 * (s + 1.0) * exp(-s);
+    }
+    return phi;
+}
+
+struct LmlGradArgs {
+    const double* Ts;     // [B][Npad][DP]
+    const double* c1c2;   // [B][2]
+    const double* alpha;  // [B][Npad]
+    const double* Kinv;   // [B][Npad][Npad] (full symmetric)
+    double* partial;      // [B][nBlocks][DP+2]
+    int N, Npad, DP, nBlocksX, nBlocksY;
+};
+
+// One CTA per 16x16 block of (i,j); per-thread pair; block reduction in shared memory (deterministic), the
+// per-block partials are summed by lml_grad_reduce_kernel.  Output order: [c1, l_1..l_DP, c2].
+template <int NU, int DP>
+__global__ void __launch_bounds__(256) lml_grad_kernel(LmlGradArgs p) {
+    __shared__ __align__(16) double ti[16][DP];
+    __shared__ __align__(16) double tj[16][DP];
+    __shared__ double red[8][DP + 2];
+    const int b = blockIdx.z;
+    const int i0 = blockIdx.y * 16, j0 = blockIdx.x * 16;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const double* __restrict__ Ts = p.Ts + int64_t(b) * p.Npad * DP;
+    for (int e = threadIdx.x; e < 16 * DP; e += 256) {
+        int r = e / DP, k = e % DP;
+        ti[r][k] = (i0 + r < p.N) ? Ts[int64_t(i0 + r) * DP + k] : 0.0;
+        tj[r][k] = (j0 + r < p.N) ? Ts[int64_t(j0 + r) * DP + k] : 0.0;
+    }
+    __syncthreads();
+    const int i = i0 + ty, j = j0 + tx;
+    double g[DP + 2];
+#pragma unroll
+    for (int k = 0; k < DP + 2; ++k) g[k] = 0.0;
+    if (i < p.N && j < p.N) {
+        const double c1 = p.c1c2[2 * b], c2 = p.c1c2[2 * b + 1];
+        const double* alpha = p.alpha + int64_t(b) * p.Npad;
+        const double w = alpha[i] * alpha[j] - p.Kinv[(int64_t(b) * p.Npad + i) * p.Npad + j];
+        double dk[DP];
+        double r2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+            double d = ti[ty][k] - tj[tx][k];
+            dk[k] = d * d;
+            r2 += dk[k];
+        }
+        const double r = sqrt(r2);
+        double phi, gor;
+        kernel_profile<NU>(r, r2, phi, gor);
+        if (i == j) phi = 1.0;
+        g[0] = w * c1 * phi;
+        const double wh = w * c1 * h_profile<NU>(r, r2, phi);
+#pragma unroll
+        for (int k = 0; k < DP; ++k) g[1 + k] = wh * dk[k];
+        g[DP + 1] = w * c2;
+    }
+    // warp reduce, then across the 8 warps
+#pragma unroll
+    for (int k = 0; k < DP + 2; ++k) {
+        double v = g[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < DP + 2) {
+        double s = 0.0;
+        for (int w8 = 0; w8 < 8; ++w8) s += red[w8][threadIdx.x];
+        const int64_t blk = int64_t(blockIdx.y) * p.nBlocksX + blockIdx.x;
+        p.partial[(int64_t(b) * p.nBlocksX * p.nBlocksY + blk) * (DP + 2) + threadIdx.x] = s;
+    }
+}
+
+// grad[b][k] = 0.5 * sum_blocks partial
+__global__ void lml_grad_reduce_kernel(const double* partial, int nBlocks, int P, double* grad) {
+    const int b = blockIdx.x, k = threadIdx.x;
+    if (k >= P) return;
+    double s = 0.0;
+    for (int i = 0; i < nBlocks; ++i) s += partial[(int64_t(b) * nBlocks + i) * P + k];
+    grad[b * P + k] = 0.5 * s;
+}
+
+// out[j][i] = in[i][j] for a square Npad matrix (batched via blockIdx.z)
+__global__ void transpose_square_kernel(const double* in, double* out, int n) {
+    __shared__ double tile[32][33];
+    const double* src = in + int64_t(blockIdx.z) * n * n;
+    double* dst = out + int64_t(blockIdx.z) * n * n;
+    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
+    for (int r = 0; r < 32; r += 8)
+        if (x < n && y + r < n) tile[threadIdx.y + r][threadIdx.x] = src[int64_t(y + r) * n + x];
+    __syncthreads();
+    x = blockIdx.y * 32 + threadIdx.x;
+    y = blockIdx.x * 32 + threadIdx.y;
+    for (int r = 0; r < 32; r += 8)
+        if (x < n && y + r < n) dst[int64_t(y + r) * n + x] = tile[threadIdx.x][threadIdx.y + r];
+}
+
+// keeps the lower triangle (row-major, rows/cols < N) and zeroes everything else
+__global__ void keep_lower_kernel(double* A, int N, int Npad) {
+    double* M = A + int64_t(blockIdx.z) * Npad * Npad;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Npad) return;
+    if (i >= N || j >= N || j > i) M[int64_t(i) * Npad + j] = 0.0;
+}
+
+__global__ void set_identity_kernel(double* A, int N, int Npad) {
+    double* M = A + int64_t(blockIdx.z) * Npad * Npad;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Npad) return;
+    M[int64_t(i) * Npad + j] = (i == j && i < N) ? 1.0 : 0.0;
+}
+
+}  // namespace aoed

@@ -1,0 +1,760 @@
+// Host side of the C ABI for the GP surrogate: handle, device residency, launch orchestration.
+// See include/aoed_b200.h for the contract of every exported function.
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/aoed_b200.h"
+#include "fit.cuh"
+#include "posterior.cuh"
+#include "trmm.cuh"
+
+using namespace aoed;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(AOED_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + \
+                                           ":" + std::to_string(__LINE__));                                   \
+    } while (0)
+
+#define CHK(expr)              \
+    do {                       \
+        int rc_ = (expr);      \
+        if (rc_ != AOED_OK) return rc_; \
+    } while (0)
+
+int pick_dp(int d) {
+    if (d <= 8) return 8;
+    if (d <= 16) return 16;
+    if (d <= 24) return 24;
+    if (d <= 32) return 32;
+    return -1;
+}
+
+struct Workspace {
+    int64_t cols = 0;  // capacity in candidates (multiple of 128)
+    double *XT = nullptr, *KsT = nullptr, *Gr = nullptr, *W = nullptr, *V = nullptr;
+    double *sumsq = nullptr, *part = nullptr, *part2 = nullptr;
+    // staging for the host-pointer API
+    double *Xc = nullptr, *oF = nullptr, *oS = nullptr, *oA = nullptr, *odF = nullptr, *odS = nullptr, *odA = nullptr;
+    double* hX = nullptr;  // pinned input staging
+};
+
+}  // namespace
+
+struct aoed_gp {
+    int device = 0, d = 0, m = 0, nu = 1, DP = 8;
+    int N = 0, Npad = 0, Kpad = 0, mTiles = 0, JS = 1, jchunk = 0;
+    bool has_train = false, has_theta = false;
+    std::vector<double> theta, y_mean, y_scale, lml, Xn, Yn;
+    // device model state
+    double *dX = nullptr, *dY = nullptr;  // [N][d], [m][Npad]
+    double *dTs = nullptr, *dAlpha = nullptr, *dEll = nullptr, *dLinv = nullptr, *dLinvT = nullptr, *dL = nullptr;
+    ModelDev* dModel = nullptr;
+    // fit scratch
+    double *dK = nullptr, *dC1C2 = nullptr, *dGradPartial = nullptr, *dGrad = nullptr;
+    int* dInfo = nullptr;
+    double* dSolverWork = nullptr;
+    int solverLwork = 0;
+    cusolverDnHandle_t solver = nullptr;
+    cublasHandle_t blas = nullptr;
+    Workspace ws[2];
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // counters
+    int64_t n_launches = 0, trmm_launches = 0;
+    double trmm_ms = 0.0, trmm_flops = 0.0;
+    bool profiling = false;
+};
+
+namespace {
+
+void free_ws(Workspace& w) {
+    double** ptrs[] = {&w.XT, &w.KsT, &w.Gr, &w.W, &w.V, &w.sumsq, &w.part, &w.part2,
+                       &w.Xc, &w.oF, &w.oS, &w.oA, &w.odF, &w.odS, &w.odA};
+    for (auto pp : ptrs) {
+        if (*pp) cudaFree(*pp);
+        *pp = nullptr;
+    }
+    if (w.hX) cudaFreeHost(w.hX);
+    w.hX = nullptr;
+    w.cols = 0;
+}
+
+void free_model(aoed_gp* gp) {
+    double** ptrs[] = {&gp->dX, &gp->dY, &gp->dTs, &gp->dAlpha, &gp->dEll, &gp->dLinv, &gp->dLinvT, &gp->dL,
+                       &gp->dK, &gp->dC1C2, &gp->dGradPartial, &gp->dGrad, &gp->dSolverWork};
+    for (auto pp : ptrs) {
+        if (*pp) cudaFree(*pp);
+        *pp = nullptr;
+    }
+    if (gp->dModel) cudaFree(gp->dModel);
+    gp->dModel = nullptr;
+    if (gp->dInfo) cudaFree(gp->dInfo);
+    gp->dInfo = nullptr;
+    free_ws(gp->ws[0]);
+    free_ws(gp->ws[1]);
+}
+
+int64_t chunk_cap() {
+    const char* e = getenv("AOED_CHUNK");
+    int64_t v = e ? atoll(e) : 4096;
+    if (v < 128) v = 128;
+    return round_up64(v, 128);
+}
+
+int ensure_ws(aoed_gp* gp, Workspace& w, int64_t cols, bool staging) {
+    cols = round_up64(cols, 128);
+    const int m = gp->m, DP = gp->DP, Npad = gp->Npad;
+    if (w.cols < cols) {
+        free_ws(w);
+        const size_t slab = size_t(m) * Npad * cols * sizeof(double);
+        CU(cudaMalloc(&w.XT, size_t(DP) * cols * sizeof(double)));
+        CU(cudaMalloc(&w.KsT, slab));
+        CU(cudaMalloc(&w.Gr, slab));
+        CU(cudaMalloc(&w.W, slab));
+        CU(cudaMalloc(&w.V, slab));
+        CU(cudaMemset(w.KsT, 0, slab));
+        CU(cudaMemset(w.Gr, 0, slab));
+        CU(cudaMemset(w.W, 0, slab));
+        CU(cudaMemset(w.V, 0, slab));
+        CU(cudaMalloc(&w.sumsq, size_t(m) * gp->mTiles * cols * sizeof(double)));
+        CU(cudaMalloc(&w.part, size_t(m) * gp->JS * (2 + DP) * cols * sizeof(double)));
+        CU(cudaMalloc(&w.part2, size_t(m) * gp->JS * (1 + DP) * cols * sizeof(double)));
+        w.cols = cols;
+    }
+    if (staging && w.Xc == nullptr) {
+        const size_t c = size_t(w.cols);
+        CU(cudaMalloc(&w.Xc, c * gp->d * sizeof(double)));
+        CU(cudaMalloc(&w.oF, c * m * sizeof(double)));
+        CU(cudaMalloc(&w.oS, c * m * sizeof(double)));
+        CU(cudaMalloc(&w.oA, c * m * sizeof(double)));
+        CU(cudaMalloc(&w.odF, c * m * gp->d * sizeof(double)));
+        CU(cudaMalloc(&w.odS, c * m * gp->d * sizeof(double)));
+        CU(cudaMalloc(&w.odA, c * m * gp->d * sizeof(double)));
+        CU(cudaMallocHost(&w.hX, c * gp->d * sizeof(double)));
+    }
+    return AOED_OK;
+}
+
+template <int NU, int DP>
+void launch_xcov(const XcovArgs& a, dim3 grid, bool grad, cudaStream_t s) {
+    if (grad)
+        xcov_kernel<NU, DP, true><<<grid, XC_THREADS, 0, s>>>(a);
+    else
+        xcov_kernel<NU, DP, false><<<grid, XC_THREADS, 0, s>>>(a);
+}
+
+template <int DP>
+void launch_xcov_nu(int nu, const XcovArgs& a, dim3 grid, bool grad, cudaStream_t s) {
+    switch (nu) {
+        case 1: launch_xcov<1, DP>(a, grid, grad, s); break;
+        case 3: launch_xcov<3, DP>(a, grid, grad, s); break;
+        case 5: launch_xcov<5, DP>(a, grid, grad, s); break;
+        default: launch_xcov<-1, DP>(a, grid, grad, s); break;
+    }
+}
+
+void launch_xcov_any(int nu, int DP, const XcovArgs& a, dim3 grid, bool grad, cudaStream_t s) {
+    switch (DP) {
+        case 8: launch_xcov_nu<8>(nu, a, grid, grad, s); break;
+        case 16: launch_xcov_nu<16>(nu, a, grid, grad, s); break;
+        case 24: launch_xcov_nu<24>(nu, a, grid, grad, s); break;
+        default: launch_xcov_nu<32>(nu, a, grid, grad, s); break;
+    }
+}
+
+void launch_gradsum(int DP, const GradsumArgs& a, dim3 grid, cudaStream_t s) {
+    switch (DP) {
+        case 8: gradsum_kernel<8><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 16: gradsum_kernel<16><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 24: gradsum_kernel<24><<<grid, XC_THREADS, 0, s>>>(a); break;
+        default: gradsum_kernel<32><<<grid, XC_THREADS, 0, s>>>(a); break;
+    }
+}
+
+template <int NU>
+void launch_kmat_dp(int DP, const KmatArgs& a, dim3 grid, cudaStream_t s) {
+    switch (DP) {
+        case 8: kmat_kernel<NU, 8><<<grid, 256, 0, s>>>(a); break;
+        case 16: kmat_kernel<NU, 16><<<grid, 256, 0, s>>>(a); break;
+        case 24: kmat_kernel<NU, 24><<<grid, 256, 0, s>>>(a); break;
+        default: kmat_kernel<NU, 32><<<grid, 256, 0, s>>>(a); break;
+    }
+}
+
+void launch_kmat(int nu, int DP, const KmatArgs& a, dim3 grid, cudaStream_t s) {
+    switch (nu) {
+        case 1: launch_kmat_dp<1>(DP, a, grid, s); break;
+        case 3: launch_kmat_dp<3>(DP, a, grid, s); break;
+        case 5: launch_kmat_dp<5>(DP, a, grid, s); break;
+        default: launch_kmat_dp<-1>(DP, a, grid, s); break;
+    }
+}
+
+template <int NU>
+void launch_lmlgrad_dp(int DP, const LmlGradArgs& a, dim3 grid, cudaStream_t s) {
+    switch (DP) {
+        case 8: lml_grad_kernel<NU, 8><<<grid, 256, 0, s>>>(a); break;
+        case 16: lml_grad_kernel<NU, 16><<<grid, 256, 0, s>>>(a); break;
+        case 24: lml_grad_kernel<NU, 24><<<grid, 256, 0, s>>>(a); break;
+        default: lml_grad_kernel<NU, 32><<<grid, 256, 0, s>>>(a); break;
+    }
+}
+
+void launch_lmlgrad(int nu, int DP, const LmlGradArgs& a, dim3 grid, cudaStream_t s) {
+    switch (nu) {
+        case 1: launch_lmlgrad_dp<1>(DP, a, grid, s); break;
+        case 3: launch_lmlgrad_dp<3>(DP, a, grid, s); break;
+        case 5: launch_lmlgrad_dp<5>(DP, a, grid, s); break;
+        default: launch_lmlgrad_dp<-1>(DP, a, grid, s); break;
+    }
+}
+
+int launch_trmm(aoed_gp* gp, bool upper, const TrmmArgs& a, int colTiles, int batch, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(trmm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TRMM_SMEM)));
+        CU(cudaFuncSetAttribute(trmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TRMM_SMEM)));
+        attr_set = true;
+    }
+    dim3 grid(a.mTiles, colTiles, batch);
+    if (gp->profiling) CU(cudaEventRecord(gp->ev0, s));
+    if (upper)
+        trmm_kernel<true><<<grid, TTHREADS, TRMM_SMEM, s>>>(a);
+    else
+        trmm_kernel<false><<<grid, TTHREADS, TRMM_SMEM, s>>>(a);
+    CU(cudaGetLastError());
+    gp->n_launches++;
+    gp->trmm_launches++;
+    // useful flops: one triangular product of an N x N factor with (colTiles*128) columns
+    gp->trmm_flops += double(batch) * double(gp->N) * (double(gp->N) + 1.0) * double(colTiles) * TN;
+    if (gp->profiling) {
+        CU(cudaEventRecord(gp->ev1, s));
+        CU(cudaEventSynchronize(gp->ev1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, gp->ev0, gp->ev1));
+        gp->trmm_ms += ms;
+    }
+    return AOED_OK;
+}
+
+struct EvalOut {
+    double *F, *S, *dF, *dS, *A, *dA;
+};
+
+// One chunk of `rows` candidates (rows <= ws.cols), device-resident, row-major input d_X[rows][d].
+int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool want_std, bool want_grad,
+               const AcqDev& acq, const EvalOut& out, cudaStream_t s) {
+    const int m = gp->m, DP = gp->DP, Npad = gp->Npad;
+    const int ldc = int(w.cols);
+    const int colTiles = int((rows + 127) / 128);
+    const int64_t slab = int64_t(Npad) * ldc;
+    {
+        const int cover = colTiles * 128;
+        transpose_x_kernel<<<(cover + 127) / 128, 128, 0, s>>>(d_X, rows, gp->d, DP, ldc, w.XT);
+        gp->n_launches++;
+    }
+    XcovArgs xa;
+    xa.XT = w.XT; xa.Ts = gp->dTs; xa.alpha = gp->dAlpha; xa.ell = gp->dEll; xa.model = gp->dModel;
+    xa.KsT = want_std ? w.KsT : nullptr;
+    xa.Gr = (want_std && want_grad) ? w.Gr : nullptr;
+    xa.part = w.part; xa.strideSlab = slab;
+    xa.N = gp->N; xa.Npad = Npad; xa.ldc = ldc; xa.JS = gp->JS; xa.jchunk = gp->jchunk;
+    launch_xcov_any(gp->nu, DP, xa, dim3(colTiles, gp->JS, m), want_grad, s);
+    gp->n_launches++;
+    CU(cudaGetLastError());
+    if (want_std) {
+        TrmmArgs t;
+        t.A = gp->dLinv; t.strideA = int64_t(Npad) * Npad; t.lda = Npad;
+        t.B = w.KsT; t.strideB = slab; t.ldb = ldc;
+        t.Out = want_grad ? w.W : nullptr; t.strideOut = slab; t.ldo = ldc;
+        t.sumsq = w.sumsq; t.strideSS = int64_t(gp->mTiles) * ldc;
+        t.M = gp->N; t.Kpad = gp->Kpad; t.mTiles = gp->mTiles;
+        CHK(launch_trmm(gp, false, t, colTiles, m, s));
+        if (want_grad) {
+            TrmmArgs u = t;
+            u.A = gp->dLinvT; u.B = w.W; u.Out = w.V; u.sumsq = nullptr;
+            CHK(launch_trmm(gp, true, u, colTiles, m, s));
+            GradsumArgs ga;
+            ga.V = w.V; ga.Gr = w.Gr; ga.Ts = gp->dTs; ga.part2 = w.part2; ga.strideSlab = slab;
+            ga.N = gp->N; ga.Npad = Npad; ga.ldc = ldc; ga.JS = gp->JS; ga.jchunk = gp->jchunk;
+            launch_gradsum(DP, ga, dim3(colTiles, gp->JS, m), s);
+            gp->n_launches++;
+            CU(cudaGetLastError());
+        }
+    }
+    EpilogueArgs e;
+    e.XT = w.XT; e.ell = gp->dEll; e.model = gp->dModel; e.part = w.part; e.part2 = w.part2; e.sumsq = w.sumsq;
+    e.F = out.F; e.S = out.S; e.dF = out.dF; e.dS = out.dS; e.A = out.A; e.dA = out.dA;
+    e.rows = rows; e.m = m; e.d = gp->d; e.DP = DP; e.ldc = ldc; e.JS = gp->JS; e.mTiles = gp->mTiles;
+    e.std = want_std; e.grad = want_grad; e.acq = acq;
+    epilogue_kernel<<<dim3(unsigned((rows + 127) / 128), m), 128, 0, s>>>(e);
+    gp->n_launches++;
+    CU(cudaGetLastError());
+    return AOED_OK;
+}
+
+int make_acq(const aoed_gp* gp, int kind, uint32_t flags, const double* param, AcqDev& acq) {
+    memset(&acq, 0, sizeof(acq));
+    acq.kind = kind;
+    acq.exact = (flags & AOED_EVAL_EXACT) ? 1 : 0;
+    if (kind < AOED_ACQ_NONE || kind > AOED_ACQ_PI) return fail(AOED_ERR_INVALID, "unknown acquisition kind");
+    if (kind == AOED_ACQ_UCB) {
+        if (!param || param[0] < 1.0) return fail(AOED_ERR_INVALID, "UCB needs n_sample >= 1");
+        acq.lam = sqrt(log(param[0]) / param[0]);
+    } else if (kind == AOED_ACQ_EI || kind == AOED_ACQ_PI) {
+        if (!param) return fail(AOED_ERR_INVALID, "EI/PI need y_min");
+        if (gp->m > 16) return fail(AOED_ERR_UNSUPPORTED, "EI/PI support n_obj <= 16");
+        for (int o = 0; o < gp->m; ++o) acq.y_min[o] = param[o];
+    }
+    return AOED_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int aoed_detail_fail(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+
+int aoed_abi_version(void) { return AOED_ABI_VERSION; }
+const char* aoed_last_error(void) { return g_err.c_str(); }
+
+int aoed_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int aoed_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return fail(AOED_ERR_INVALID, "null out");
+    CU(cudaMallocHost(out, bytes ? bytes : 8));
+    return AOED_OK;
+}
+
+int aoed_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return AOED_OK;
+}
+
+int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu) {
+    if (!out) return fail(AOED_ERR_INVALID, "null out");
+    if (aoed_device_count() <= device || device < 0)
+        return fail(AOED_ERR_NO_DEVICE, "no CUDA device " + std::to_string(device) + " (there is no CPU fallback)");
+    if (n_var < 1 || n_obj < 1) return fail(AOED_ERR_INVALID, "n_var and n_obj must be positive");
+    if (!(nu == 1 || nu == 3 || nu == 5 || nu == -1)) return fail(AOED_ERR_INVALID, "nu must be 1, 3, 5 or -1");
+    const int DP = pick_dp(n_var);
+    if (DP < 0) return fail(AOED_ERR_UNSUPPORTED, "n_var > 32 is not supported yet");
+    CU(cudaSetDevice(device));
+    aoed_gp* gp = new aoed_gp();
+    gp->device = device; gp->d = n_var; gp->m = n_obj; gp->nu = nu; gp->DP = DP;
+    CU(cudaStreamCreateWithFlags(&gp->streams[0], cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&gp->streams[1], cudaStreamNonBlocking));
+    CU(cudaEventCreate(&gp->ev0));
+    CU(cudaEventCreate(&gp->ev1));
+    if (cusolverDnCreate(&gp->solver) != CUSOLVER_STATUS_SUCCESS) return fail(AOED_ERR_CUDA, "cusolverDnCreate failed");
+    if (cublasCreate(&gp->blas) != CUBLAS_STATUS_SUCCESS) return fail(AOED_ERR_CUDA, "cublasCreate failed");
+    *out = gp;
+    return AOED_OK;
+}
+
+int aoed_gp_destroy(aoed_gp_t* gp) {
+    if (!gp) return AOED_OK;
+    cudaSetDevice(gp->device);
+    cudaDeviceSynchronize();
+    free_model(gp);
+    if (gp->solver) cusolverDnDestroy(gp->solver);
+    if (gp->blas) cublasDestroy(gp->blas);
+    if (gp->ev0) cudaEventDestroy(gp->ev0);
+    if (gp->ev1) cudaEventDestroy(gp->ev1);
+    for (auto& s : gp->streams)
+        if (s) cudaStreamDestroy(s);
+    delete gp;
+    return AOED_OK;
+}
+
+int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const double* h_Yn, const double* h_y_mean,
+                      const double* h_y_scale) {
+    if (!gp || !h_Xn || !h_Yn) return fail(AOED_ERR_INVALID, "null argument");
+    if (n_train < 1) return fail(AOED_ERR_INVALID, "n_train must be positive");
+    CU(cudaSetDevice(gp->device));
+    CU(cudaDeviceSynchronize());
+    free_model(gp);
+    const int N = n_train, d = gp->d, m = gp->m;
+    gp->N = N;
+    gp->Npad = round_up(N, TM);
+    gp->Kpad = round_up(N, TK);
+    gp->mTiles = gp->Npad / TM;
+    gp->JS = std::min(16, std::max(1, (N + 255) / 256));
+    gp->jchunk = round_up((N + gp->JS - 1) / gp->JS, XC_JT);
+    gp->JS = (N + gp->jchunk - 1) / gp->jchunk;
+    gp->has_train = true;
+    gp->has_theta = false;
+    gp->Xn.assign(h_Xn, h_Xn + size_t(N) * d);
+    gp->Yn.assign(h_Yn, h_Yn + size_t(N) * m);
+    gp->y_mean.assign(m, 0.0);
+    gp->y_scale.assign(m, 1.0);
+    if (h_y_mean) gp->y_mean.assign(h_y_mean, h_y_mean + m);
+    if (h_y_scale) gp->y_scale.assign(h_y_scale, h_y_scale + m);
+    gp->lml.assign(m, std::numeric_limits<double>::quiet_NaN());
+    const size_t Np = gp->Npad;
+    CU(cudaMalloc(&gp->dX, size_t(N) * d * sizeof(double)));
+    CU(cudaMemcpy(gp->dX, h_Xn, size_t(N) * d * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<double> yt(size_t(m) * Np, 0.0);
+    for (int o = 0; o < m; ++o)
+        for (int i = 0; i < N; ++i) yt[size_t(o) * Np + i] = h_Yn[size_t(i) * m + o];
+    CU(cudaMalloc(&gp->dY, yt.size() * sizeof(double)));
+    CU(cudaMemcpy(gp->dY, yt.data(), yt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&gp->dTs, size_t(m) * Np * gp->DP * sizeof(double)));
+    CU(cudaMalloc(&gp->dAlpha, size_t(m) * Np * sizeof(double)));
+    CU(cudaMalloc(&gp->dEll, size_t(m) * gp->DP * sizeof(double)));
+    CU(cudaMalloc(&gp->dModel, size_t(m) * sizeof(ModelDev)));
+    CU(cudaMalloc(&gp->dLinv, size_t(m) * Np * Np * sizeof(double)));
+    CU(cudaMalloc(&gp->dLinvT, size_t(m) * Np * Np * sizeof(double)));
+    CU(cudaMalloc(&gp->dL, size_t(m) * Np * Np * sizeof(double)));
+    CU(cudaMalloc(&gp->dK, Np * Np * sizeof(double)));
+    CU(cudaMalloc(&gp->dC1C2, size_t(m) * 2 * sizeof(double)));
+    CU(cudaMalloc(&gp->dInfo, sizeof(int)));
+    const int nb = (N + 15) / 16;
+    CU(cudaMalloc(&gp->dGradPartial, size_t(nb) * nb * (gp->DP + 2) * sizeof(double)));
+    CU(cudaMalloc(&gp->dGrad, size_t(gp->DP + 2) * sizeof(double)));
+    int lwork = 0;
+    if (cusolverDnDpotrf_bufferSize(gp->solver, CUBLAS_FILL_MODE_UPPER, N, gp->dK, gp->Npad, &lwork) !=
+        CUSOLVER_STATUS_SUCCESS)
+        return fail(AOED_ERR_CUDA, "potrf_bufferSize failed");
+    gp->solverLwork = lwork;
+    CU(cudaMalloc(&gp->dSolverWork, size_t(std::max(lwork, 1)) * sizeof(double)));
+    return AOED_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Uploads Ts = X / l (padded), c1/c2 for ONE hyper-parameter vector into slot `slot` of the per-objective arrays.
+int upload_theta_slot(aoed_gp* gp, int slot, const double* theta, cudaStream_t s) {
+    const int d = gp->d, DP = gp->DP, N = gp->N;
+    const size_t Np = gp->Npad;
+    std::vector<double> ell(DP, 1.0);
+    for (int k = 0; k < d; ++k) ell[k] = exp(theta[1 + k]);
+    std::vector<double> ts(Np * DP, 0.0);
+    for (int i = 0; i < N; ++i)
+        for (int k = 0; k < d; ++k) ts[size_t(i) * DP + k] = gp->Xn[size_t(i) * d + k] / ell[k];
+    double c12[2] = {exp(theta[0]), exp(theta[d + 1])};
+    CU(cudaMemcpyAsync(gp->dTs + size_t(slot) * Np * DP, ts.data(), ts.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(gp->dEll + size_t(slot) * DP, ell.data(), DP * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(gp->dC1C2 + size_t(slot) * 2, c12, 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));  // host vectors go out of scope
+    return AOED_OK;
+}
+
+// K(theta) of objective slot -> gp->dK, Cholesky in place (row-major lower).  info != 0 => not PD.
+int factor_slot(aoed_gp* gp, int slot, int* info, cudaStream_t s) {
+    const int N = gp->N, Npad = gp->Npad;
+    CU(cudaMemsetAsync(gp->dK, 0, size_t(Npad) * Npad * sizeof(double), s));
+    KmatArgs ka;
+    ka.Ts = gp->dTs + size_t(slot) * Npad * gp->DP;
+    ka.c1c2 = gp->dC1C2 + size_t(slot) * 2;
+    ka.K = gp->dK; ka.N = N; ka.Npad = Npad; ka.DP = gp->DP;
+    const int nb = (N + 15) / 16;
+    launch_kmat(gp->nu, gp->DP, ka, dim3(nb, nb, 1), s);
+    gp->n_launches++;
+    CU(cudaGetLastError());
+    cusolverDnSetStream(gp->solver, s);
+    // row-major lower L  <=>  column-major upper U = L^T with K = U^T U
+    if (cusolverDnDpotrf(gp->solver, CUBLAS_FILL_MODE_UPPER, N, gp->dK, Npad, gp->dSolverWork, gp->solverLwork,
+                         gp->dInfo) != CUSOLVER_STATUS_SUCCESS)
+        return fail(AOED_ERR_CUDA, "cusolverDnDpotrf failed");
+    CU(cudaMemcpyAsync(info, gp->dInfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return AOED_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int aoed_gp_set_theta(aoed_gp_t* gp, const double* h_theta) {
+    if (!gp || !h_theta) return fail(AOED_ERR_INVALID, "null argument");
+    if (!gp->has_train) return fail(AOED_ERR_INVALID, "set_train must be called before set_theta");
+    CU(cudaSetDevice(gp->device));
+    cudaStream_t s = gp->streams[0];
+    const int N = gp->N, Npad = gp->Npad, m = gp->m, d = gp->d, p = d + 2;
+    const size_t NN = size_t(Npad) * Npad;
+    gp->theta.assign(h_theta, h_theta + size_t(m) * p);
+    gp->has_theta = false;
+    cublasSetStream(gp->blas, s);
+    std::vector<ModelDev> md(m);
+    for (int o = 0; o < m; ++o) {
+        const double* th = h_theta + size_t(o) * p;
+        CHK(upload_theta_slot(gp, o, th, s));
+        int info = 0;
+        CHK(factor_slot(gp, o, &info, s));
+        if (info != 0)
+            return fail(AOED_ERR_NOT_PD, "kernel matrix of objective " + std::to_string(o) +
+                                             " is not positive definite at the given theta (leading minor " +
+                                             std::to_string(info) + ")");
+        double* L = gp->dL + o * NN;
+        CU(cudaMemcpyAsync(L, gp->dK, NN * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        keep_lower_kernel<<<dim3((Npad + 127) / 128, Npad, 1), 128, 0, s>>>(L, N, Npad);
+        // alpha = K^-1 y
+        double* alpha = gp->dAlpha + size_t(o) * Npad;
+        CU(cudaMemcpyAsync(alpha, gp->dY + size_t(o) * Npad, size_t(Npad) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        if (cusolverDnDpotrs(gp->solver, CUBLAS_FILL_MODE_UPPER, N, 1, gp->dK, Npad, alpha, Npad, gp->dInfo) !=
+            CUSOLVER_STATUS_SUCCESS)
+            return fail(AOED_ERR_CUDA, "cusolverDnDpotrs failed");
+        // L^-1 (row-major) = column-major U^-1 :  solve U X = I
+        double* Linv = gp->dLinv + o * NN;
+        set_identity_kernel<<<dim3((Npad + 127) / 128, Npad, 1), 128, 0, s>>>(Linv, N, Npad);
+        const double one = 1.0;
+        if (cublasDtrsm(gp->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, N, N,
+                        &one, gp->dK, Npad, Linv, Npad) != CUBLAS_STATUS_SUCCESS)
+            return fail(AOED_ERR_CUDA, "cublasDtrsm failed");
+        keep_lower_kernel<<<dim3((Npad + 127) / 128, Npad, 1), 128, 0, s>>>(Linv, N, Npad);
+        transpose_square_kernel<<<dim3(Npad / 32, Npad / 32, 1), dim3(32, 8), 0, s>>>(Linv, gp->dLinvT + o * NN, Npad);
+        gp->n_launches += 4;
+        CU(cudaGetLastError());
+        // log marginal likelihood value at theta (_gpr.py:601-616)
+        std::vector<double> hal(N), hdiag(N);
+        CU(cudaMemcpyAsync(hal.data(), alpha, size_t(N) * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpy2DAsync(hdiag.data(), sizeof(double), L, (size_t(Npad) + 1) * sizeof(double), sizeof(double), N,
+                             cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        double quad = 0.0, logdet = 0.0;
+        for (int i = 0; i < N; ++i) {
+            quad += gp->Yn[size_t(i) * m + o] * hal[i];
+            logdet += log(hdiag[i]);
+        }
+        gp->lml[o] = -0.5 * quad - logdet - 0.5 * N * log(2.0 * M_PI);
+        md[o].c1 = exp(th[0]);
+        md[o].c2 = exp(th[d + 1]);
+        md[o].y_mean = gp->y_mean[o];
+        md[o].y_scale = gp->y_scale[o];
+    }
+    CU(cudaMemcpyAsync(gp->dModel, md.data(), m * sizeof(ModelDev), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    gp->has_theta = true;
+    return AOED_OK;
+}
+
+int aoed_gp_get_state(aoed_gp_t* gp, int obj, double* h_L, double* h_alpha, double* h_lml) {
+    if (!gp || !gp->has_theta) return fail(AOED_ERR_INVALID, "model has no fitted state");
+    if (obj < 0 || obj >= gp->m) return fail(AOED_ERR_INVALID, "objective index out of range");
+    CU(cudaSetDevice(gp->device));
+    const int N = gp->N, Npad = gp->Npad;
+    if (h_L)
+        CU(cudaMemcpy2D(h_L, size_t(N) * sizeof(double), gp->dL + size_t(obj) * Npad * Npad, size_t(Npad) * sizeof(double),
+                        size_t(N) * sizeof(double), N, cudaMemcpyDeviceToHost));
+    if (h_alpha)
+        CU(cudaMemcpy(h_alpha, gp->dAlpha + size_t(obj) * Npad, size_t(N) * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_lml) *h_lml = gp->lml[obj];
+    return AOED_OK;
+}
+
+int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const double* h_theta, double* h_lml,
+                      double* h_grad) {
+    if (!gp || !h_obj || !h_theta || !h_lml) return fail(AOED_ERR_INVALID, "null argument");
+    if (!gp->has_train) return fail(AOED_ERR_INVALID, "set_train must be called first");
+    CU(cudaSetDevice(gp->device));
+    cudaStream_t s = gp->streams[0];
+    const int N = gp->N, Npad = gp->Npad, m = gp->m, d = gp->d, p = d + 2, DP = gp->DP;
+    const size_t NN = size_t(Npad) * Npad;
+    cublasSetStream(gp->blas, s);
+    // scratch: slot 0 of the per-objective arrays is reused problem by problem, so a later
+    // set_theta is required before evaluating (has_theta is cleared).
+    gp->has_theta = false;
+    double* Kinv = gp->dLinv;       // scratch
+    double* alpha = gp->dAlpha;     // scratch [Npad]
+    for (int b = 0; b < n_prob; ++b) {
+        const int o = h_obj[b];
+        if (o < 0 || o >= m) return fail(AOED_ERR_INVALID, "objective index out of range");
+        const double* th = h_theta + size_t(b) * p;
+        CHK(upload_theta_slot(gp, 0, th, s));
+        int info = 0;
+        CHK(factor_slot(gp, 0, &info, s));
+        if (info != 0) {  // _gpr.py:589-593
+            h_lml[b] = -std::numeric_limits<double>::infinity();
+            if (h_grad)
+                for (int k = 0; k < p; ++k) h_grad[size_t(b) * p + k] = 0.0;
+            continue;
+        }
+        CU(cudaMemcpyAsync(alpha, gp->dY + size_t(o) * Npad, size_t(Npad) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        if (cusolverDnDpotrs(gp->solver, CUBLAS_FILL_MODE_UPPER, N, 1, gp->dK, Npad, alpha, Npad, gp->dInfo) !=
+            CUSOLVER_STATUS_SUCCESS)
+            return fail(AOED_ERR_CUDA, "cusolverDnDpotrs failed");
+        std::vector<double> hal(N), hdiag(N);
+        CU(cudaMemcpyAsync(hal.data(), alpha, size_t(N) * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpy2DAsync(hdiag.data(), sizeof(double), gp->dK, (size_t(Npad) + 1) * sizeof(double), sizeof(double),
+                             N, cudaMemcpyDeviceToHost, s));
+        if (h_grad) {
+            // K^-1 = solve against the identity (what sklearn does, _gpr.py:631-633)
+            set_identity_kernel<<<dim3((Npad + 127) / 128, Npad, 1), 128, 0, s>>>(Kinv, N, Npad);
+            if (cusolverDnDpotrs(gp->solver, CUBLAS_FILL_MODE_UPPER, N, N, gp->dK, Npad, Kinv, Npad, gp->dInfo) !=
+                CUSOLVER_STATUS_SUCCESS)
+                return fail(AOED_ERR_CUDA, "cusolverDnDpotrs (inverse) failed");
+            LmlGradArgs ga;
+            ga.Ts = gp->dTs; ga.c1c2 = gp->dC1C2; ga.alpha = alpha; ga.Kinv = Kinv; ga.partial = gp->dGradPartial;
+            ga.N = N; ga.Npad = Npad; ga.DP = DP;
+            const int nb = (N + 15) / 16;
+            ga.nBlocksX = nb; ga.nBlocksY = nb;
+            launch_lmlgrad(gp->nu, DP, ga, dim3(nb, nb, 1), s);
+            lml_grad_reduce_kernel<<<1, DP + 2, 0, s>>>(gp->dGradPartial, nb * nb, DP + 2, gp->dGrad);
+            gp->n_launches += 3;
+            CU(cudaGetLastError());
+            std::vector<double> hg(DP + 2);
+            CU(cudaMemcpyAsync(hg.data(), gp->dGrad, (DP + 2) * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            double* g = h_grad + size_t(b) * p;
+            g[0] = hg[0];
+            for (int k = 0; k < d; ++k) g[1 + k] = hg[1 + k];
+            g[d + 1] = hg[DP + 1];
+        } else {
+            CU(cudaStreamSynchronize(s));
+        }
+        double quad = 0.0, logdet = 0.0;
+        for (int i = 0; i < N; ++i) {
+            quad += gp->Yn[size_t(i) * m + o] * hal[i];
+            logdet += log(hdiag[i]);
+        }
+        h_lml[b] = -0.5 * quad - logdet - 0.5 * N * log(2.0 * M_PI);
+    }
+    (void)NN;
+    return AOED_OK;
+}
+
+static int eval_common(aoed_gp_t* gp, int64_t n_rows, uint32_t flags, int acq_kind, const double* h_acq_param,
+                       bool& want_std, bool& want_grad, AcqDev& acq, const void* hF, const void* hS) {
+    if (!gp) return fail(AOED_ERR_INVALID, "null handle");
+    if (!gp->has_theta) return fail(AOED_ERR_INVALID, "surrogate model is not fitted yet");
+    if (n_rows < 0) return fail(AOED_ERR_INVALID, "negative row count");
+    if (flags & AOED_EVAL_HESS) {
+        if (hF == nullptr && hS == nullptr) {}
+    }
+    want_std = (flags & AOED_EVAL_STD) != 0 || acq_kind >= AOED_ACQ_UCB;
+    want_grad = (flags & AOED_EVAL_GRAD) != 0;
+    CHK(make_acq(gp, acq_kind, flags, h_acq_param, acq));
+    return AOED_OK;
+}
+
+int aoed_gp_eval_device(aoed_gp_t* gp, int64_t n_rows, const double* d_Xn, uint32_t flags, int acq_kind,
+                        const double* h_acq_param, double* d_F, double* d_S, double* d_dF, double* d_dS,
+                        double* d_hF, double* d_hS, double* d_A, double* d_dA, double* d_hA, void* stream) {
+    bool want_std, want_grad;
+    AcqDev acq;
+    CHK(eval_common(gp, n_rows, flags, acq_kind, h_acq_param, want_std, want_grad, acq, d_hF, d_hS));
+    if (flags & AOED_EVAL_HESS) return fail(AOED_ERR_UNSUPPORTED, "hessian path: use aoed_gp_eval (host API)");
+    (void)d_hF; (void)d_hS; (void)d_hA;
+    if (n_rows == 0) return AOED_OK;
+    if (!d_Xn) return fail(AOED_ERR_INVALID, "null input");
+    CU(cudaSetDevice(gp->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t cap = std::min<int64_t>(chunk_cap(), round_up64(n_rows, 128));
+    CHK(ensure_ws(gp, gp->ws[0], cap, false));
+    Workspace& w = gp->ws[0];
+    const int m = gp->m, d = gp->d;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += w.cols) {
+        const int64_t rows = std::min<int64_t>(w.cols, n_rows - r0);
+        EvalOut out;
+        out.F = d_F ? d_F + r0 * m : nullptr;
+        out.S = d_S ? d_S + r0 * m : nullptr;
+        out.A = d_A ? d_A + r0 * m : nullptr;
+        out.dF = d_dF ? d_dF + r0 * m * d : nullptr;
+        out.dS = d_dS ? d_dS + r0 * m * d : nullptr;
+        out.dA = d_dA ? d_dA + r0 * m * d : nullptr;
+        CHK(eval_chunk(gp, w, d_Xn + r0 * d, rows, want_std, want_grad, acq, out, s));
+    }
+    return AOED_OK;
+}
+
+int aoed_gp_eval(aoed_gp_t* gp, int64_t n_rows, const double* h_Xn, uint32_t flags, int acq_kind,
+                 const double* h_acq_param, double* h_F, double* h_S, double* h_dF, double* h_dS, double* h_hF,
+                 double* h_hS, double* h_A, double* h_dA, double* h_hA) {
+    bool want_std, want_grad;
+    AcqDev acq;
+    CHK(eval_common(gp, n_rows, flags, acq_kind, h_acq_param, want_std, want_grad, acq, h_hF, h_hS));
+    if (flags & AOED_EVAL_HESS) return fail(AOED_ERR_UNSUPPORTED, "hessian kernels not built yet");
+    (void)h_hF; (void)h_hS; (void)h_hA;
+    if (n_rows == 0) return AOED_OK;
+    if (!h_Xn) return fail(AOED_ERR_INVALID, "null input");
+    CU(cudaSetDevice(gp->device));
+    const int m = gp->m, d = gp->d;
+    const int64_t cap = std::min<int64_t>(chunk_cap(), round_up64(n_rows, 128));
+    const int nslots = (n_rows > cap) ? 2 : 1;
+    for (int i = 0; i < nslots; ++i) CHK(ensure_ws(gp, gp->ws[i], cap, true));
+    int slot = 0;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += cap, slot ^= 1) {
+        Workspace& w = gp->ws[slot];
+        cudaStream_t s = gp->streams[slot];
+        const int64_t rows = std::min<int64_t>(cap, n_rows - r0);
+        // the slot's previous chunk must have drained before its staging buffers are reused
+        CU(cudaStreamSynchronize(s));
+        memcpy(w.hX, h_Xn + r0 * d, size_t(rows) * d * sizeof(double));
+        CU(cudaMemcpyAsync(w.Xc, w.hX, size_t(rows) * d * sizeof(double), cudaMemcpyHostToDevice, s));
+        EvalOut out;
+        out.F = h_F ? w.oF : nullptr;
+        out.S = (h_S && want_std) ? w.oS : nullptr;
+        out.A = h_A ? w.oA : nullptr;
+        out.dF = (h_dF && want_grad) ? w.odF : nullptr;
+        out.dS = (h_dS && want_grad && want_std) ? w.odS : nullptr;
+        out.dA = (h_dA && want_grad) ? w.odA : nullptr;
+        CHK(eval_chunk(gp, w, w.Xc, rows, want_std, want_grad, acq, out, s));
+        const size_t b1 = size_t(rows) * m * sizeof(double), b2 = b1 * d;
+        if (out.F) CU(cudaMemcpyAsync(h_F + r0 * m, w.oF, b1, cudaMemcpyDeviceToHost, s));
+        if (out.S) CU(cudaMemcpyAsync(h_S + r0 * m, w.oS, b1, cudaMemcpyDeviceToHost, s));
+        if (out.A) CU(cudaMemcpyAsync(h_A + r0 * m, w.oA, b1, cudaMemcpyDeviceToHost, s));
+        if (out.dF) CU(cudaMemcpyAsync(h_dF + r0 * m * d, w.odF, b2, cudaMemcpyDeviceToHost, s));
+        if (out.dS) CU(cudaMemcpyAsync(h_dS + r0 * m * d, w.odS, b2, cudaMemcpyDeviceToHost, s));
+        if (out.dA) CU(cudaMemcpyAsync(h_dA + r0 * m * d, w.odA, b2, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(gp->streams[0]));
+    CU(cudaStreamSynchronize(gp->streams[1]));
+    return AOED_OK;
+}
+
+int aoed_gp_set_profiling(aoed_gp_t* gp, int on) {
+    if (!gp) return fail(AOED_ERR_INVALID, "null handle");
+    gp->profiling = on != 0;
+    return AOED_OK;
+}
+
+int aoed_gp_get_counters(aoed_gp_t* gp, int64_t* n_launches, double* trmm_ms, int64_t* trmm_launches,
+                         double* trmm_flops) {
+    if (!gp) return fail(AOED_ERR_INVALID, "null handle");
+    if (n_launches) *n_launches = gp->n_launches;
+    if (trmm_ms) *trmm_ms = gp->trmm_ms;
+    if (trmm_launches) *trmm_launches = gp->trmm_launches;
+    if (trmm_flops) *trmm_flops = gp->trmm_flops;
+    return AOED_OK;
+}
+
+int aoed_gp_reset_counters(aoed_gp_t* gp) {
+    if (!gp) return fail(AOED_ERR_INVALID, "null handle");
+    gp->n_launches = gp->trmm_launches = 0;
+    gp->trmm_ms = gp->trmm_flops = 0.0;
+    return AOED_OK;
+}
+
+}  // extern "C"

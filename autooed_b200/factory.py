@@ -1,0 +1,47 @@
+"""Name -> class maps with the reference's factory names (`autooed/mobo/factory.py:11-22, 25-38, 74-86`), so that
+a maintainer can route 'gp' / 'ei' / 'identity' / 'pi' / 'ucb' / 'hvi' to the B200 path."""
+from autooed_b200.surrogate_model import GaussianProcess
+from autooed_b200.acquisition import Identity, UpperConfidenceBound, ExpectedImprovement, ProbabilityOfImprovement
+from autooed_b200.selection import HypervolumeImprovement
+
+_SURROGATES = {'gp': GaussianProcess}
+_ACQUISITIONS = {'ei': ExpectedImprovement, 'identity': Identity, 'pi': ProbabilityOfImprovement,
+                 'ucb': UpperConfidenceBound}
+_SELECTIONS = {'hvi': HypervolumeImprovement}
+
+
+def get_surrogate_model(name):
+    if name in _SURROGATES:
+        return _SURROGATES[name]
+    raise Exception(f'Undefined surrogate model {name}')
+
+
+def get_acquisition(name):
+    if name in _ACQUISITIONS:
+        return _ACQUISITIONS[name]
+    raise Exception(f'Undefined acquisition function {name}')
+
+
+def get_selection(name):
+    if name in _SELECTIONS:
+        return _SELECTIONS[name]
+    raise Exception(f'Undefined selection {name}')
+
+
+def _name(name, params, key):
+    # the CLI spells module_cfg[...]['surrogate'], GUI configs use ['name'] (SURVEY.md §5 "Config / flag system")
+    if name is not None:
+        return name
+    return params[key] if key in params else params['name']
+
+
+def init_surrogate_model(name, params, problem):
+    return get_surrogate_model(_name(name, params, 'surrogate'))(problem, **params)
+
+
+def init_acquisition(name, params, surrogate_model):
+    return get_acquisition(_name(name, params, 'acquisition'))(surrogate_model, **params)
+
+
+def init_selection(name, params, surrogate_model):
+    return get_selection(_name(name, params, 'selection'))(surrogate_model, **params)

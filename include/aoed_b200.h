@@ -1,0 +1,138 @@
+/*
+ * aoed_b200.h — C ABI of the B200-native GP-surrogate hot path of AutoOED.
+ *
+ * One shared library (libaoed_b200.so, built from autooed_b200/csrc/ for sm_100a) exports exactly
+ * these entry points.  Plain pointers and sizes only: no torch / numpy types cross this boundary.
+ * Every function returns AOED_OK (0) or a negative AOED_ERR_* code; aoed_last_error() gives the text.
+ *
+ * Conventions
+ *   - all floating point is IEEE float64, all matrices are C-contiguous row-major (rows, features),
+ *     exactly the numpy arrays the reference passes around (SURVEY.md §8b "Data conventions");
+ *   - "normalised" X means clip((X - xl)/(xu - xl), 0, 1) and normalised Y means (Y - mean)/std, i.e.
+ *     what autooed/utils/normalization.py:31-32,103-109 produces before `GaussianProcess._fit/_evaluate`;
+ *   - theta is the sklearn log-parameter vector [log c1, log l_1..l_d, log c2] (p = d + 2) of the kernel
+ *     c1 * Matern_nu(l) + c2 built at autooed/mobo/surrogate_model/gp.py:126-132; nu in {1,3,5,-1};
+ *   - pointers named h_* are HOST pointers, d_* are DEVICE pointers on the handle's device.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the AutoOED tree).
+ */
+#ifndef AOED_B200_H
+#define AOED_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AOED_ABI_VERSION 1
+
+/* return codes */
+#define AOED_OK 0
+#define AOED_ERR_INVALID (-1)   /* bad argument / unfitted model (the reference's AssertionError) */
+#define AOED_ERR_CUDA (-2)      /* CUDA runtime failure (message in aoed_last_error) */
+#define AOED_ERR_NOT_PD (-3)    /* Cholesky of K failed at the final theta (numpy.linalg.LinAlgError in sklearn _gpr.py:352-361) */
+#define AOED_ERR_UNSUPPORTED (-4)
+#define AOED_ERR_NO_DEVICE (-5) /* no CUDA device: there is NO CPU fallback */
+
+/* evaluate flags (autooed/mobo/surrogate_model/base.py:68 `evaluate(X, std, gradient, hessian)`) */
+#define AOED_EVAL_STD 1u
+#define AOED_EVAL_GRAD 2u
+#define AOED_EVAL_HESS 4u
+#define AOED_EVAL_EXACT 8u /* exact derivatives instead of the reference's literal broadcasting */
+
+/* acquisition kinds (autooed/mobo/factory.py:25-38) */
+#define AOED_ACQ_NONE 0
+#define AOED_ACQ_IDENTITY 1 /* acquisition/identity.py:15-18 */
+#define AOED_ACQ_UCB 2      /* acquisition/ucb.py:19-53, param[0] = n_sample */
+#define AOED_ACQ_EI 3       /* acquisition/ei.py:20-70,  param[0..m) = y_min */
+#define AOED_ACQ_PI 4       /* acquisition/pi.py:20-64,  param[0..m) = y_min */
+
+typedef struct aoed_gp aoed_gp_t; /* opaque: one multi-objective GP surrogate resident on one GPU */
+
+/* ---- library ------------------------------------------------------------------------------ */
+int aoed_abi_version(void);
+const char* aoed_last_error(void);
+int aoed_device_count(void);
+/* pinned host memory so that result arrays can be copied back asynchronously */
+int aoed_host_alloc(void** out, uint64_t bytes);
+int aoed_host_free(void* p);
+
+/* ---- model lifecycle ------------------------------------------------------------------------
+ * replaces GaussianProcess.__init__ (gp.py:108-135): n_obj independent GPs, kernel selected by nu. */
+int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu);
+int aoed_gp_destroy(aoed_gp_t* gp);
+
+/* replaces the data hand-off of GaussianProcess._fit (gp.py:137-139) after SurrogateModel.fit normalised
+ * the data (base.py:31-52): Xn (n_train x n_var), Yn (n_train x n_obj), plus the StandardScaler statistics
+ * used by SurrogateModel.evaluate to un-normalise (base.py:106-109). */
+int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const double* h_Yn,
+                      const double* h_y_mean, const double* h_y_scale);
+
+/* replaces sklearn GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True)
+ * (_gpr.py:541-655, reached from gp.py:139) for a BATCH of `n_prob` independent problems at once:
+ * problem b uses objective h_obj[b] and hyper-parameters h_theta[b*p .. b*p+p).
+ * Outputs h_lml[b] (-inf when K is not PD, with zero gradient, as _gpr.py:589-593) and h_grad[b*p..]. */
+int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const double* h_theta,
+                      double* h_lml, double* h_grad /* may be NULL */);
+
+/* replaces the tail of GaussianProcessRegressor.fit (_gpr.py:349-367): fixes theta (n_obj x p), factorises
+ * K = k(X,X) + 1e-10 I, computes alpha_ and caches L^-1 for the posterior.  AOED_ERR_NOT_PD on failure. */
+int aoed_gp_set_theta(aoed_gp_t* gp, const double* h_theta);
+
+/* sklearn attributes other AutoOED modules read (`gp.L_`, `gp.alpha_`, `log_marginal_likelihood_value_`):
+ * h_L (n_train x n_train lower, row-major), h_alpha (n_train); either may be NULL. */
+int aoed_gp_get_state(aoed_gp_t* gp, int obj, double* h_L, double* h_alpha, double* h_lml);
+
+/* ---- posterior + acquisition ------------------------------------------------------------------
+ * replaces GaussianProcess._evaluate (gp.py:141-253) + the un-normalisation of SurrogateModel.evaluate
+ * (base.py:106-109) + `<Acquisition>._evaluate` (identity.py / ucb.py / ei.py / pi.py) in ONE call.
+ *   h_Xn      : n_rows x n_var normalised candidates
+ *   flags     : AOED_EVAL_* (batched semantics = stack of per-row reference results)
+ *   acq_kind  : AOED_ACQ_*; h_acq_param as documented above (NULL for NONE / IDENTITY)
+ * Outputs (any may be NULL = not wanted; shapes as base.py:87-92):
+ *   F, S  : n_rows x n_obj          dF, dS : n_rows x n_obj x n_var      hF, hS : n_rows x n_obj x n_var x n_var
+ *   A, dA, hA : acquisition value / gradient / hessian with the same shapes as F, dF, hF
+ * F, S, dF, dS are in raw-Y units; hF, hS stay in normalised-Y units unless AOED_EVAL_EXACT.
+ * Host buffers; host<->device copies happen inside, chunked and overlapped with compute. */
+int aoed_gp_eval(aoed_gp_t* gp, int64_t n_rows, const double* h_Xn, uint32_t flags, int acq_kind,
+                 const double* h_acq_param, double* h_F, double* h_S, double* h_dF, double* h_dS,
+                 double* h_hF, double* h_hS, double* h_A, double* h_dA, double* h_hA);
+
+/* same computation with DEVICE-resident input and outputs (no PCIe traffic), enqueued on `stream`
+ * (a cudaStream_t; NULL = default stream).  Used by bench.py's `value` leg and by multi-GPU sharding. */
+int aoed_gp_eval_device(aoed_gp_t* gp, int64_t n_rows, const double* d_Xn, uint32_t flags, int acq_kind,
+                        const double* h_acq_param, double* d_F, double* d_S, double* d_dF, double* d_dS,
+                        double* d_hF, double* d_hS, double* d_A, double* d_dA, double* d_hA, void* stream);
+
+/* counters for bench.py: number of kernels this handle launched, and the accumulated device time (ms) of the
+ * dominant kernel family (triangular FP64 GEMM) measured with CUDA events when profiling is switched on. */
+int aoed_gp_set_profiling(aoed_gp_t* gp, int on);
+int aoed_gp_get_counters(aoed_gp_t* gp, int64_t* n_launches, double* trmm_ms, int64_t* trmm_launches,
+                         double* trmm_flops);
+int aoed_gp_reset_counters(aoed_gp_t* gp);
+
+/* ---- multi-objective selection ------------------------------------------------------------------
+ * replaces find_pareto_front / check_pareto (autooed/utils/pareto.py:27-62): non-dominated mask of Y (n x m),
+ * minimisation; i is kept iff no j has all(Y_j <= Y_i) and any(Y_j < Y_i). */
+int aoed_pareto_mask(int device, int64_t n, int m, const double* h_Y, uint8_t* h_mask);
+/* non-dominated sorting rank (0 = first front), pymoo NonDominatedSorting semantics. */
+int aoed_pareto_rank(int device, int64_t n, int m, const double* h_Y, int32_t* h_rank);
+
+/* replaces HypervolumeImprovement._select (autooed/mobo/selection/hvi.py:16-47): greedy batch of `batch`
+ * candidate indices maximising the exclusive hypervolume w.r.t. the running front (initially h_front,
+ * n_front x m), reference point h_ref (m).  Strict '>' so the lowest index wins ties (hvi.py:35-37);
+ * when no candidate has a positive contribution the entry is -1 and the caller draws the random fallback
+ * (hvi.py:38-39) with the host RNG, then calls again with the updated front (see selection/hvi.py in the
+ * Python package).  h_contrib (batch) receives the winning contributions (may be NULL). */
+int aoed_hvi_select(int device, int64_t n_cand, int m, const double* h_Yc, int64_t n_front,
+                    const double* h_front, const double* h_ref, int batch, const uint8_t* h_excluded,
+                    int64_t* h_idx, double* h_contrib);
+/* exclusive hypervolume contribution of every candidate w.r.t. a fixed front (one greedy round). */
+int aoed_hv_contributions(int device, int64_t n_cand, int m, const double* h_Yc, int64_t n_front,
+                          const double* h_front, const double* h_ref, double* h_contrib);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AOED_B200_H */

@@ -1,0 +1,85 @@
+"""GPU parity of Pareto filtering and hypervolume-improvement selection against the CPU oracle
+(bit-exact indices: SURVEY.md §8 a16-a17)."""
+import numpy as np
+import pytest
+
+from oracle import moo_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,m", [(1, 2), (50, 2), (300, 3), (1000, 3), (257, 4), (64, 1)])
+def test_pareto_mask_and_front(n, m):
+    from autooed_b200.utils import pareto
+    rng = np.random.default_rng(n * 10 + m)
+    Y = rng.random((n, m))
+    Y[n // 2:] = np.round(Y[n // 2:], 1)  # plenty of ties and duplicates
+    assert np.array_equal(pareto.check_pareto(Y), mo.check_pareto(Y))
+    front, idx = pareto.find_pareto_front(Y, return_index=True)
+    ofront, oidx = mo.find_pareto_front(Y, return_index=True)
+    assert sorted(idx) == sorted(int(i) for i in oidx)  # argsort is not stable: compare sets
+    assert np.array_equal(np.sort(front, axis=0), np.sort(ofront, axis=0))
+    assert np.array_equal(pareto.pareto_rank(Y), mo.pareto_rank(Y))
+
+
+def test_pareto_empty():
+    from autooed_b200.utils import pareto
+    assert len(pareto.find_pareto_front(np.empty((0, 2)))) == 0
+
+
+@pytest.mark.parametrize("m", [2, 3, 4])
+def test_hv_contributions_vs_oracle(m):
+    from autooed_b200.utils import pareto
+    rng = np.random.default_rng(m)
+    Y = rng.random((60, m)) + 0.2
+    Yc = rng.random((400, m)) * 1.2
+    front = mo.find_pareto_front(Y)
+    ref = np.max(np.vstack([Yc, Y]), axis=0)
+    got = pareto.hv_contributions(Yc, front, ref)
+    want = mo.hv_contributions(Yc, front, ref)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-15)
+    base = mo.hypervolume(front, ref)
+    diff = np.array([mo.hypervolume(np.vstack([front, y]), ref) - base for y in Yc[:50]])
+    assert np.allclose(got[:50], diff, rtol=1e-9, atol=1e-13)
+    assert ((got == 0) == (want == 0)).all()  # dominated candidates are exactly zero
+    assert abs(pareto.calc_hypervolume(Y, ref) - base) < 1e-12 * max(1.0, base)
+
+
+@pytest.mark.parametrize("m,C,N,batch", [(2, 200, 40, 10), (3, 500, 60, 20), (2, 30, 200, 8), (4, 100, 30, 5)])
+def test_hvi_select_same_batch(m, C, N, batch):
+    from autooed_b200.selection.hvi import hvi_select_indices
+    rng = np.random.default_rng(100 * m + C)
+    Y = rng.random((N, m)) + 0.15
+    Yc = rng.random((C, m))
+    Yc[C // 2:] = Yc[: C - C // 2]  # duplicates: the lowest index must win ties (hvi.py:35-37)
+    np.random.seed(7)
+    want = mo.hvi_select(Yc, Y, batch)
+    np.random.seed(7)
+    got = hvi_select_indices(Yc, Y, batch)
+    assert list(got) == want
+
+
+def test_hvi_random_fallback_same_seed():
+    """All candidates dominated by the data: every pick is the reference's np.random.choice (hvi.py:38-39)."""
+    from autooed_b200.selection.hvi import hvi_select_indices
+    rng = np.random.default_rng(3)
+    Y = rng.random((30, 2)) * 0.1
+    Yc = rng.random((20, 2)) * 0.5 + 0.5
+    np.random.seed(11)
+    want = mo.hvi_select(Yc, Y, 6)
+    np.random.seed(11)
+    got = hvi_select_indices(Yc, Y, 6)
+    assert list(got) == want
+
+
+def test_selection_class_pads_and_transforms():
+    from autooed_b200 import GaussianProcess, HypervolumeImprovement
+    from autooed_b200.problem import SimpleProblem
+    rng = np.random.default_rng(5)
+    gp = GaussianProcess(SimpleProblem(4, 2))
+    sel = HypervolumeImprovement(gp)
+    X, Y = rng.random((20, 4)), rng.random((20, 2)) + 0.3
+    Xc, Yc = rng.random((3, 4)), rng.random((3, 2))
+    np.random.seed(0)
+    X_next = sel.select(Xc, Yc, X, Y, 5)  # fewer candidates than the batch: padded (selection/base.py:46-50)
+    assert X_next.shape == (5, 4)
