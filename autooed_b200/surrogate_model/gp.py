@@ -346,6 +346,25 @@ class GaussianProcess(SurrogateModel):
                         want_surrogate=False)
         return out['A'], out['dA'], out['hA']
 
+    def evaluate_device(self, d_X, n_rows, std=True, gradient=True, acq_kind=_lib.ACQ_NONE, acq_param=None,
+                        exact=False, d_F=None, d_S=None, d_dF=None, d_dS=None, d_A=None, d_dA=None, stream=None):
+        """Device-resident evaluation (no PCIe traffic): every `d_*` is a device pointer (int) or an object with
+        `.data_ptr()` (e.g. a float64 torch tensor on this model's GPU) holding normalised candidates / receiving
+        the outputs in the layouts of `evaluate`.  Enqueued on `stream` (cudaStream_t as int; None = legacy default)."""
+        assert self.fitted, 'Surrogate model is not fitted yet'
+        lib, h = _lib.load(), self._ensure_handle()
+
+        def dp(t):
+            if t is None:
+                return None
+            return ctypes.c_void_p(int(t.data_ptr()) if hasattr(t, 'data_ptr') else int(t))
+
+        flags = (_lib.EVAL_STD if std else 0) | (_lib.EVAL_GRAD if gradient else 0) | (_lib.EVAL_EXACT if exact else 0)
+        param = None if acq_param is None else _lib.as_f64(acq_param)
+        _lib.check(lib.aoed_gp_eval_device(h, int(n_rows), dp(d_X), flags, acq_kind, _lib.ptr(param), dp(d_F), dp(d_S),
+                                           dp(d_dF), dp(d_dS), None, None, dp(d_A), dp(d_dA), None,
+                                           ctypes.c_void_p(stream) if stream else None))
+
     # ---- benchmark hooks -------------------------------------------------------------------------------------
     def counters(self):
         lib, h = _lib.load(), self._ensure_handle()

@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Benchmark of the GP-surrogate hot path (BASELINE.json metric: GP posterior+grad candidate evals/sec).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One step = one pass of the hot path over one batch of synthetic candidates: for every candidate and all n_obj
+objectives the posterior mean, std, d mean/dx, d std/dx and the fused UCB acquisition value + gradient.
+Workload: N=2000 training points, d=20, n_obj=3, Matern-5/2, 2^20 candidates per GPU.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is produced.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gp_posterior_grad_candidate_evals_per_sec"
+UNIT = "evals/s"
+WORKLOAD = dict(workload="c4: synthetic GP N=2000 d=20 n_obj=3, Matern-5/2, UCB value+gradient over 2^20 candidates per GPU",
+                n_train=2000, n_var=20, n_obj=3, nu=5, acquisition="ucb", candidates_per_gpu=1 << 20,
+                l2_policy="working set per step (K*, W, V, Gr slabs: 805 MB per chunk; outputs 528 MB) exceeds the 126 MB L2")
+
+
+def make_problem(n_train, d, m, seed=0):
+    """Synthetic data of SURVEY.md §8(d): X ~ U[0,1]^{N x d}, Y = sin(XW) + 0.1 X^2 |W|; fixed hyper-parameters."""
+    rng = np.random.default_rng(seed)
+    X = rng.random((n_train, d))
+    W = rng.standard_normal((d, m))
+    Y = np.sin(X @ W) + 0.1 * (X ** 2) @ np.abs(W)
+    rng1 = np.random.default_rng(seed + 1)
+    thetas = np.stack([np.concatenate([[0.0], rng1.uniform(-0.5, 1.0, d), [math.log(0.01)]]) for _ in range(m)])
+    return X, Y, thetas
+
+
+def candidates(n, d, seed):
+    return np.random.default_rng(seed).random((n, d))
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_rate(n_train, d, m, nu, budget_s, chunk=1024):
+    """The CPU oracle (vectorised numpy restatement of gp.py:141-253 + ucb.py) on a bounded sample of the workload."""
+    from oracle import gp_oracle as go
+    X, Y, thetas = make_problem(n_train, d, m)
+    orc = go.GPOracle(d, m, nu=nu).fit(X, Y, thetas=thetas)
+    for st in orc.states:
+        st.Kinv  # K^-1 formed once outside the timed region, as the reference caches gp._K_inv (gp.py:154-157)
+    Xs = candidates(chunk, d, 2)
+    val = orc.evaluate(Xs[:64], std=True, gradient=True, var_form="kinv", chunk=64)  # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        # the reference's own formulation: one dense GEMM against the explicit inverse (gp.py:160-161, 201-205)
+        val = orc.evaluate(Xs, std=True, gradient=True, var_form="kinv", chunk=512)
+        go.acquisition("ucb", val, True, False, n_sample=n_train)
+        done += chunk
+        el = time.perf_counter() - t0
+        if el >= budget_s:
+            break
+    return done / el, done, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOAD
+    cores = os.cpu_count()
+    rates = []
+    for _ in range(args.warmup):
+        cpu_port_rate(w["n_train"], w["n_var"], w["n_obj"], w["nu"], 1.0)
+    t_tot, n_tot = 0.0, 0
+    for _ in range(args.steps):
+        rate, done, el = cpu_port_rate(w["n_train"], w["n_var"], w["n_obj"], w["nu"], args.cpu_seconds)
+        rates.append(rate); t_tot += el; n_tot += done
+    value = n_tot / t_tot
+    sample = f"{n_tot // max(args.steps, 1)} candidates per step of the c4 workload (time-bounded {args.cpu_seconds}s per step)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(w),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def dgemm_peak(torch, dev):
+    n = 8192
+    a = torch.randn(n, n, device=dev, dtype=torch.float64)
+    b = torch.randn(n, n, device=dev, dtype=torch.float64)
+    c = torch.empty_like(a)
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    return 2.0 * n ** 3 / best * 1e-9
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from autooed_b200 import GaussianProcess, UpperConfidenceBound, _lib
+    from autooed_b200.problem import SimpleProblem
+    import __graft_entry__ as ge
+    ge.build()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    w = WORKLOAD
+    N, d, m, C = w["n_train"], w["n_var"], w["n_obj"], args.candidates or w["candidates_per_gpu"]
+
+    X, Y, thetas = make_problem(N, d, m)
+    gp = GaussianProcess(SimpleProblem(d, m), nu=w["nu"], device=local)
+    gp.fit_fixed(X, Y, thetas)
+    acq = UpperConfidenceBound(gp)
+    acq.fit(X, Y)
+    Xs = candidates(C, d, 2 + rank)  # every rank owns its own shard of candidates (weak scaling, no data-path collective)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg (`value`) --------------------------------------------------------------------
+    dX = torch.from_numpy(Xs).to(dev)
+    dA = torch.empty((C, m), dtype=torch.float64, device=dev)
+    ddA = torch.empty((C, m, d), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        gp.evaluate_device(dX, C, std=True, gradient=True, acq_kind=_lib.ACQ_UCB, acq_param=[float(N)], d_A=dA, d_dA=ddA,
+                           stream=stream)
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    gp.reset_counters()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    launches = gp.counters()["launches"]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end leg (`e2e`): public API, host numpy in / host numpy out -----------------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        acq.evaluate(Xs, dtype='normalized', gradient=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        F, dF, _ = acq.evaluate(Xs, dtype='normalized', gradient=True)
+    e1.record()
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = t.tolist()
+
+    # numerics guard: device leg and host leg agree
+    same = bool(np.allclose(dA.cpu().numpy(), F, rtol=0, atol=0))
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (triangular FP64 DMMA product), timed with events per launch -------
+        gp.set_profiling(True)
+        gp.reset_counters()
+        step_device()
+        torch.cuda.synchronize()
+        cnt = gp.counters()
+        gp.set_profiling(False)
+        achieved = cnt["trmm_flops"] / (cnt["trmm_ms"] * 1e-3) * 1e-12
+        peak = dgemm_peak(torch, dev)
+        step_ms_profiled = cnt["trmm_ms"]
+        roofline = {"bound": "tensor", "kernel": "trmm_kernel (FP64 DMMA m8n8k4 triangular product)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": "cuBLAS DGEMM fp64 8192^3 measured live in this run (MEASURED_PEAKS.json holds HBM and bf16 "
+                                   "only; FP64 DMMA issue peak measured at 37.2 TFLOP/s, profiles/fp64_pipe_probe_r01.json)",
+                    "flops_per_launch": cnt["trmm_flops"] / max(cnt["trmm_launches"], 1),
+                    "avg_launch_ms": cnt["trmm_ms"] / max(cnt["trmm_launches"], 1),
+                    "kernel_share_of_step": step_ms_profiled / (ms_dev / args.steps)}
+        cpu_rate, cpu_done, cpu_el = cpu_port_rate(N, d, m, w["nu"], args.cpu_seconds)
+        total = C * world * args.steps
+        value = total / (ms_dev * 1e-3)
+        e2e_value = total / (ms_e2e * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": dict(w, candidates_per_gpu=C, parallelism=f"candidate-shard x{world}"),
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": C * d * 8,
+                        "d2h_bytes_per_step": C * m * (1 + d) * 8},
+                "gpu_launches": launches, "roofline": roofline,
+                "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                 "sample": f"{cpu_done} candidates of the same workload in {cpu_el:.1f}s (oracle/gp_oracle.py, numpy BLAS threads unrestricted)"},
+                "clocks": clocks, "device_host_legs_identical": same}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU per step (default 2^20)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sample budget per step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

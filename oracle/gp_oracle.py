@@ -23,6 +23,7 @@ import math
 import numpy as np
 from scipy.linalg import cho_solve, cholesky, solve_triangular
 from scipy.optimize import minimize
+from scipy.spatial.distance import cdist
 from scipy.special import ndtr
 
 JITTER = 1e-10  # sklearn GaussianProcessRegressor(alpha=1e-10) default, used by gp.py:134
@@ -53,12 +54,7 @@ def _split_theta(theta):
 
 def _scaled_dist(A, B, ell):
     """r = cdist(A/l, B/l) by direct differences (gp.py:33,175) — not the |a|^2+|b|^2-2ab form."""
-    As, Bs = A / ell, B / ell
-    r2 = np.zeros((A.shape[0], B.shape[0]))
-    for k in range(A.shape[1]):
-        diff = As[:, k, None] - Bs[None, :, k]
-        r2 += diff * diff
-    return np.sqrt(r2)
+    return cdist(A / ell, B / ell, metric="euclidean")
 
 
 def _phi(r, nu):
