@@ -237,12 +237,14 @@ int launch_trmm(aoed_gp* gp, bool upper, const TrmmArgs& a, int colTiles, int ba
         CU(cudaFuncSetAttribute(trmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TRMM_SMEM)));
         attr_set = true;
     }
-    dim3 grid(a.mTiles, colTiles, batch);
+    TrmmArgs args = a;
+    args.colTiles = colTiles;
+    dim3 grid(colTiles * batch, a.mTiles, 1);
     if (gp->profiling) CU(cudaEventRecord(gp->ev0, s));
     if (upper)
-        trmm_kernel<true><<<grid, TTHREADS, TRMM_SMEM, s>>>(a);
+        trmm_kernel<true><<<grid, TTHREADS, TRMM_SMEM, s>>>(args);
     else
-        trmm_kernel<false><<<grid, TTHREADS, TRMM_SMEM, s>>>(a);
+        trmm_kernel<false><<<grid, TTHREADS, TRMM_SMEM, s>>>(args);
     CU(cudaGetLastError());
     gp->n_launches++;
     gp->trmm_launches++;

@@ -43,6 +43,7 @@ struct TrmmArgs {
     int M;       // valid rows
     int Kpad;    // valid k rounded up to TK
     int mTiles;
+    int colTiles;
 };
 
 template <bool UPPER>
@@ -51,9 +52,11 @@ __global__ void __launch_bounds__(TTHREADS, 1) trmm_kernel(TrmmArgs p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
     const int g = lane >> 2, q = lane & 3;
-    // heaviest row tiles are scheduled first
-    const int mt = UPPER ? int(blockIdx.x) : (p.mTiles - 1 - int(blockIdx.x));
-    const int ct = blockIdx.y, batch = blockIdx.z;
+    // Work per CTA grows with the k-range of its row tile.  CTAs are dispatched in linear block order, so the row
+    // tile is the SLOW grid index, heaviest first: every heavy tile of the launch starts before any light one and the
+    // light tiles fill the tail (longest-processing-time-first).
+    const int mt = UPPER ? int(blockIdx.y) : (p.mTiles - 1 - int(blockIdx.y));
+    const int ct = int(blockIdx.x) % p.colTiles, batch = int(blockIdx.x) / p.colTiles;
     const double* __restrict__ A = p.A + batch * p.strideA + int64_t(mt) * TM * p.lda;
     const double* __restrict__ B = p.B + batch * p.strideB + int64_t(ct) * TN;
     const int k_begin = UPPER ? mt * TM : 0;
