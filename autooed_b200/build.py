@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libaoed_b200.so")
 SOURCES = ["gp.cu", "moo.cu"]
-HEADERS = ["common.cuh", "trmm.cuh", "posterior.cuh", "fit.cuh", os.path.join("..", "..", "include", "aoed_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "aoed_b200.h")]
 
 
 def _nvcc():

@@ -62,7 +62,7 @@ struct LmlGradArgs {
     const double* Ts;     // [B][Npad][DP]
     const double* c1c2;   // [B][2]
     const double* alpha;  // [B][Npad]
-    const double* Kinv;   // [B][Npad][Npad] (full symmetric)
+    const double* Kinv;   // [B][Npad][Npad] (row-major lower triangle valid)
     double* partial;      // [B][nBlocks][DP+2]
     int N, Npad, DP, nBlocksX, nBlocksY;
 };
@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) lml_grad_kernel(LmlGradArgs p) {
     if (i < p.N && j < p.N) {
         const double c1 = p.c1c2[2 * b], c2 = p.c1c2[2 * b + 1];
         const double* alpha = p.alpha + int64_t(b) * p.Npad;
-        const double w = alpha[i] * alpha[j] - p.Kinv[(int64_t(b) * p.Npad + i) * p.Npad + j];
+        // K^-1 comes from potri: only the row-major LOWER triangle is valid, read it symmetrically
+        const double w = alpha[i] * alpha[j] - p.Kinv[(int64_t(b) * p.Npad + max(i, j)) * p.Npad + min(i, j)];
         double dk[DP];
         double r2 = 0.0;
 #pragma unroll
@@ -127,13 +128,68 @@ __global__ void __launch_bounds__(256) lml_grad_kernel(LmlGradArgs p) {
     }
 }
 
-// grad[b][k] = 0.5 * sum_blocks partial
-__global__ void lml_grad_reduce_kernel(const double* partial, int nBlocks, int P, double* grad) {
-    const int b = blockIdx.x, k = threadIdx.x;
-    if (k >= P) return;
+// res[1 + k] = 0.5 * sum_blocks partial (k in the theta order [c1, l_1..l_d, c2]); zeros when the factorisation failed.
+// One CTA per component k (deterministic tree reduction).
+__global__ void __launch_bounds__(256) lml_grad_reduce_kernel(const double* __restrict__ partial, int nBlocks, int DP, int d,
+                                                              const int* info, double* res) {
+    __shared__ double red[8];
+    const int k = blockIdx.x;
     double s = 0.0;
-    for (int i = 0; i < nBlocks; ++i) s += partial[(int64_t(b) * nBlocks + i) * P + k];
-    grad[b * P + k] = 0.5 * s;
+    for (int i = threadIdx.x; i < nBlocks; i += 256) s += partial[int64_t(i) * (DP + 2) + k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    s = (*info != 0) ? 0.0 : 0.5 * s;
+    if (k == 0) res[1] = s;
+    else if (k == DP + 1) res[1 + d + 1] = s;
+    else if (k - 1 < d) res[1 + k] = s;
+}
+
+// Ts = X / l (padded to DP), c1c2 = exp(theta[0]), exp(theta[d+1]) for one hyper-parameter vector (device-side, no host sync)
+__global__ void theta_prep_kernel(const double* __restrict__ X, const double* __restrict__ theta, int N, int Npad, int d,
+                                  int DP, double* __restrict__ Ts, double* __restrict__ c1c2) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) {
+        c1c2[0] = exp(theta[0]);
+        c1c2[1] = exp(theta[d + 1]);
+    }
+    if (idx >= Npad * DP) return;
+    const int i = idx / DP, k = idx % DP;
+    Ts[idx] = (i < N && k < d) ? X[int64_t(i) * d + k] / exp(theta[1 + k]) : 0.0;
+}
+
+// res[0] = -1/2 y.alpha - sum log L_ii - N/2 log 2 pi   (_gpr.py:601-616); -inf when potrf reported a non-PD matrix
+__global__ void __launch_bounds__(256) lml_value_kernel(const double* __restrict__ y, const double* __restrict__ alpha,
+                                                        const double* __restrict__ Lfac, int N, int Npad, const int* info,
+                                                        double* res) {
+    __shared__ double red[2][8];
+    double q = 0.0, ld = 0.0;
+    for (int i = threadIdx.x; i < N; i += 256) {
+        q = fma(y[i], alpha[i], q);
+        ld += log(Lfac[int64_t(i) * Npad + i]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        q += __shfl_xor_sync(0xffffffffu, q, off);
+        ld += __shfl_xor_sync(0xffffffffu, ld, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = q;
+        red[1][threadIdx.x >> 5] = ld;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double qq = 0.0, ll = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            qq += red[0][w];
+            ll += red[1][w];
+        }
+        res[0] = (*info != 0) ? -INFINITY : -0.5 * qq - ll - 0.5 * N * 1.8378770664093453;
+    }
 }
 
 // out[j][i] = in[i][j] for a square Npad matrix (batched via blockIdx.z)

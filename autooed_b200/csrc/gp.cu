@@ -14,6 +14,8 @@
 
 #include "../../include/aoed_b200.h"
 #include "fit.cuh"
+#include "fit_small.cuh"
+#include "hessian.cuh"
 #include "posterior.cuh"
 #include "trmm.cuh"
 
@@ -57,9 +59,23 @@ struct Workspace {
     // staging for the host-pointer API
     double *Xc = nullptr, *oF = nullptr, *oS = nullptr, *oA = nullptr, *odF = nullptr, *odS = nullptr, *odA = nullptr;
     double* hX = nullptr;  // pinned input staging
+    // Hessian path (lazily allocated): |L^-1 dk_i|^2 partials, Gram matrices, internal first-order outputs, staging
+    int64_t hrows = 0;
+    double *sumsq2 = nullptr, *gram = nullptr, *bF = nullptr, *bS = nullptr, *bdF = nullptr, *bdS = nullptr;
+    double *ohF = nullptr, *ohS = nullptr, *ohA = nullptr;
 };
 
 }  // namespace
+
+// per-stream scratch of the blocked (large-N) log-marginal-likelihood path
+struct FitCtx {
+    cudaStream_t stream = nullptr;
+    cusolverDnHandle_t solver = nullptr;
+    double *K = nullptr, *Ts = nullptr, *c1c2 = nullptr, *alpha = nullptr, *partial = nullptr, *work = nullptr;
+    int* info = nullptr;
+    int lwork = 0;
+};
+constexpr int kMaxFitCtx = 4;
 
 struct aoed_gp {
     int device = 0, d = 0, m = 0, nu = 1, DP = 8;
@@ -77,6 +93,12 @@ struct aoed_gp {
     int solverLwork = 0;
     cusolverDnHandle_t solver = nullptr;
     cublasHandle_t blas = nullptr;
+    FitCtx fit[kMaxFitCtx];
+    int nfit = 0;
+    double *dThetaB = nullptr, *dResB = nullptr;  // batched LML inputs / results
+    int* dObjB = nullptr;
+    int batchCap = 0;
+    int64_t n_fit_small = 0, n_fit_blocked = 0;
     Workspace ws[2];
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -90,7 +112,8 @@ namespace {
 
 void free_ws(Workspace& w) {
     double** ptrs[] = {&w.XT, &w.KsT, &w.Gr, &w.W, &w.V, &w.sumsq, &w.part, &w.part2,
-                       &w.Xc, &w.oF, &w.oS, &w.oA, &w.odF, &w.odS, &w.odA};
+                       &w.Xc, &w.oF, &w.oS, &w.oA, &w.odF, &w.odS, &w.odA,
+                       &w.sumsq2, &w.gram, &w.bF, &w.bS, &w.bdF, &w.bdS, &w.ohF, &w.ohS, &w.ohA};
     for (auto pp : ptrs) {
         if (*pp) cudaFree(*pp);
         *pp = nullptr;
@@ -98,6 +121,7 @@ void free_ws(Workspace& w) {
     if (w.hX) cudaFreeHost(w.hX);
     w.hX = nullptr;
     w.cols = 0;
+    w.hrows = 0;
 }
 
 void free_model(aoed_gp* gp) {
@@ -111,6 +135,27 @@ void free_model(aoed_gp* gp) {
     gp->dModel = nullptr;
     if (gp->dInfo) cudaFree(gp->dInfo);
     gp->dInfo = nullptr;
+    for (int i = 0; i < gp->nfit; ++i) {
+        FitCtx& c = gp->fit[i];
+        double** fp[] = {&c.K, &c.Ts, &c.c1c2, &c.alpha, &c.partial, &c.work};
+        for (auto pp : fp) {
+            if (*pp) cudaFree(*pp);
+            *pp = nullptr;
+        }
+        if (c.info) cudaFree(c.info);
+        c.info = nullptr;
+        if (c.solver) cusolverDnDestroy(c.solver);
+        c.solver = nullptr;
+        if (c.stream) cudaStreamDestroy(c.stream);
+        c.stream = nullptr;
+    }
+    gp->nfit = 0;
+    if (gp->dThetaB) cudaFree(gp->dThetaB);
+    if (gp->dResB) cudaFree(gp->dResB);
+    if (gp->dObjB) cudaFree(gp->dObjB);
+    gp->dThetaB = gp->dResB = nullptr;
+    gp->dObjB = nullptr;
+    gp->batchCap = 0;
     free_ws(gp->ws[0]);
     free_ws(gp->ws[1]);
 }
@@ -332,6 +377,115 @@ int make_acq(const aoed_gp* gp, int kind, uint32_t flags, const double* param, A
     return AOED_OK;
 }
 
+template <int NU>
+void launch_hess_dp(int DP, const HessArgs& a, dim3 grid, cudaStream_t s) {
+    switch (DP) {
+        case 8: hess_kernel<NU, 8><<<grid, HS_THREADS, 0, s>>>(a); break;
+        case 16: hess_kernel<NU, 16><<<grid, HS_THREADS, 0, s>>>(a); break;
+        case 24: hess_kernel<NU, 24><<<grid, HS_THREADS, 0, s>>>(a); break;
+        default: hess_kernel<NU, 32><<<grid, HS_THREADS, 0, s>>>(a); break;
+    }
+}
+
+void launch_hess(int nu, int DP, const HessArgs& a, dim3 grid, cudaStream_t s) {
+    switch (nu) {
+        case 1: launch_hess_dp<1>(DP, a, grid, s); break;
+        case 3: launch_hess_dp<3>(DP, a, grid, s); break;
+        case 5: launch_hess_dp<5>(DP, a, grid, s); break;
+        default: launch_hess_dp<-1>(DP, a, grid, s); break;
+    }
+}
+
+// rows of candidates per chunk on the Hessian path: the d k*/dx_i right-hand sides take rows*d slab columns
+int64_t hess_rows_cap(const aoed_gp* gp, int64_t n_rows) {
+    const int64_t by_cols = std::max<int64_t>(1, chunk_cap() / gp->d);
+    return std::max<int64_t>(1, std::min<int64_t>(n_rows, by_cols));
+}
+
+int ensure_ws_hess(aoed_gp* gp, Workspace& w, int64_t hrows, bool staging) {
+    CHK(ensure_ws(gp, w, round_up64(hrows * gp->d, 128), staging));
+    const size_t m = gp->m, d = gp->d;
+    if (w.hrows < hrows) {
+        double** ptrs[] = {&w.sumsq2, &w.gram, &w.bF, &w.bS, &w.bdF, &w.bdS, &w.ohF, &w.ohS, &w.ohA};
+        for (auto pp : ptrs) {
+            if (*pp) cudaFree(*pp);
+            *pp = nullptr;
+        }
+        const size_t r = size_t(hrows);
+        CU(cudaMalloc(&w.sumsq2, m * gp->mTiles * size_t(w.cols) * sizeof(double)));
+        CU(cudaMalloc(&w.gram, m * r * d * d * sizeof(double)));
+        CU(cudaMalloc(&w.bF, r * m * sizeof(double)));
+        CU(cudaMalloc(&w.bS, r * m * sizeof(double)));
+        CU(cudaMalloc(&w.bdF, r * m * d * sizeof(double)));
+        CU(cudaMalloc(&w.bdS, r * m * d * sizeof(double)));
+        w.hrows = hrows;
+    }
+    if (staging && w.ohF == nullptr) {
+        const size_t n = size_t(w.hrows) * m * d * d * sizeof(double);
+        CU(cudaMalloc(&w.ohF, n));
+        CU(cudaMalloc(&w.ohS, n));
+        CU(cudaMalloc(&w.ohA, n));
+    }
+    return AOED_OK;
+}
+
+struct HessOut {
+    double *hF, *hS, *hA;
+};
+
+// One chunk with second derivatives: first-order pipeline (always with gradients: the variance Hessian and the
+// EI / PI Hessians need them, gp.py:236-241), then the d k*/dx_i triangular product and the fused Hessian kernel.
+int eval_hess_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool want_std, const AcqDev& acq,
+                    const EvalOut& out, const HessOut& hout, cudaStream_t s) {
+    const int m = gp->m, d = gp->d, DP = gp->DP, Npad = gp->Npad;
+    const int ldc = int(w.cols);
+    const int64_t slab = int64_t(Npad) * ldc;
+    EvalOut in = out;  // first-order results are inputs of the Hessian kernel: route through internal buffers if unwanted
+    if (!in.F) in.F = w.bF;
+    if (!in.dF) in.dF = w.bdF;
+    if (want_std) {
+        if (!in.S) in.S = w.bS;
+        if (!in.dS) in.dS = w.bdS;
+    }
+    CHK(eval_chunk(gp, w, d_X, rows, want_std, true, acq, in, s));
+    const bool exact = acq.exact != 0;
+    if (want_std) {
+        DkcolArgs da;
+        da.XT = w.XT; da.Ts = gp->dTs; da.ell = gp->dEll; da.Gr = w.Gr; da.DK = w.KsT; da.strideSlab = slab;
+        da.rows = int(rows); da.d = d; da.DP = DP; da.N = gp->N; da.Npad = Npad; da.ldc = ldc; da.ldx = ldc;
+        da.JS = gp->JS; da.jchunk = gp->jchunk;
+        const int colTiles = int((rows * d + 127) / 128);
+        dkcol_kernel<<<dim3(colTiles, gp->JS, m), 128, 0, s>>>(da);
+        gp->n_launches++;
+        CU(cudaGetLastError());
+        TrmmArgs t;
+        t.A = gp->dLinv; t.strideA = int64_t(Npad) * Npad; t.lda = Npad;
+        t.B = w.KsT; t.strideB = slab; t.ldb = ldc;
+        t.Out = exact ? w.W : nullptr; t.strideOut = slab; t.ldo = ldc;
+        t.sumsq = exact ? nullptr : w.sumsq2; t.strideSS = int64_t(gp->mTiles) * ldc;
+        t.M = gp->N; t.Kpad = gp->Kpad; t.mTiles = gp->mTiles;
+        CHK(launch_trmm(gp, false, t, colTiles, m, s));
+        if (exact) {
+            GramArgs ga;
+            ga.W = w.W; ga.G = w.gram; ga.strideSlab = slab; ga.rows = int(rows); ga.d = d; ga.N = gp->N; ga.ldc = ldc;
+            gram_kernel<<<dim3(unsigned(rows), m), HS_THREADS, 0, s>>>(ga);
+            gp->n_launches++;
+            CU(cudaGetLastError());
+        }
+    }
+    HessArgs h;
+    h.XT = w.XT; h.Ts = gp->dTs; h.ell = gp->dEll; h.alpha = gp->dAlpha; h.model = gp->dModel;
+    h.V = w.V; h.sumsq = w.sumsq; h.mid_ss = w.sumsq2; h.gram = w.gram;
+    h.F = in.F; h.S = in.S; h.dF = in.dF; h.dS = in.dS;
+    h.hF = hout.hF; h.hS = want_std ? hout.hS : nullptr; h.hA = hout.hA;
+    h.strideSlab = slab; h.rows = int(rows); h.m = m; h.d = d; h.N = gp->N; h.Npad = Npad; h.ldc = ldc; h.ldx = ldc;
+    h.mTiles = gp->mTiles; h.std = want_std ? 1 : 0; h.acq = acq;
+    launch_hess(gp->nu, DP, h, dim3(unsigned(rows), m), s);
+    gp->n_launches++;
+    CU(cudaGetLastError());
+    return AOED_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -495,6 +649,81 @@ int factor_slot(aoed_gp* gp, int slot, int* info, cudaStream_t s) {
     return AOED_OK;
 }
 
+
+int ensure_batch(aoed_gp* gp, int n_prob) {
+    if (gp->batchCap >= n_prob) return AOED_OK;
+    if (gp->dThetaB) cudaFree(gp->dThetaB);
+    if (gp->dResB) cudaFree(gp->dResB);
+    if (gp->dObjB) cudaFree(gp->dObjB);
+    const int cap = std::max(n_prob, 64);
+    const size_t p = gp->d + 2;
+    CU(cudaMalloc(&gp->dThetaB, size_t(cap) * p * sizeof(double)));
+    CU(cudaMalloc(&gp->dResB, size_t(cap) * (p + 1) * sizeof(double)));
+    CU(cudaMalloc(&gp->dObjB, size_t(cap) * sizeof(int)));
+    gp->batchCap = cap;
+    return AOED_OK;
+}
+
+int ensure_fit_ctx(aoed_gp* gp) {
+    if (gp->nfit > 0) return AOED_OK;
+    const int N = gp->N, Npad = gp->Npad, DP = gp->DP;
+    const int n = (N <= 1024) ? kMaxFitCtx : 2;  // small problems do not fill the GPU alone: overlap them
+    const size_t NN = size_t(Npad) * Npad;
+    const int nb = (N + 15) / 16;
+    for (int i = 0; i < n; ++i) {
+        FitCtx& c = gp->fit[i];
+        CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        if (cusolverDnCreate(&c.solver) != CUSOLVER_STATUS_SUCCESS) return fail(AOED_ERR_CUDA, "cusolverDnCreate failed");
+        cusolverDnSetStream(c.solver, c.stream);
+        CU(cudaMalloc(&c.K, NN * sizeof(double)));
+        CU(cudaMemsetAsync(c.K, 0, NN * sizeof(double), c.stream));
+        CU(cudaMalloc(&c.Ts, size_t(Npad) * DP * sizeof(double)));
+        CU(cudaMalloc(&c.c1c2, 2 * sizeof(double)));
+        CU(cudaMalloc(&c.alpha, size_t(Npad) * sizeof(double)));
+        CU(cudaMalloc(&c.partial, size_t(nb) * nb * (DP + 2) * sizeof(double)));
+        CU(cudaMalloc(&c.info, 2 * sizeof(int)));
+        int l1 = 0, l2 = 0;
+        if (cusolverDnDpotrf_bufferSize(c.solver, CUBLAS_FILL_MODE_UPPER, N, c.K, Npad, &l1) != CUSOLVER_STATUS_SUCCESS ||
+            cusolverDnDpotri_bufferSize(c.solver, CUBLAS_FILL_MODE_UPPER, N, c.K, Npad, &l2) != CUSOLVER_STATUS_SUCCESS)
+            return fail(AOED_ERR_CUDA, "cusolver bufferSize failed");
+        c.lwork = std::max(std::max(l1, l2), 1);
+        CU(cudaMalloc(&c.work, size_t(c.lwork) * sizeof(double)));
+        gp->nfit = i + 1;
+    }
+    return AOED_OK;
+}
+
+template <int NU>
+int launch_lml_small_dp(int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t s) {
+    const size_t sm = lml_small_smem(a.N, DP);
+#define FS_CASE(D)                                                                                              \
+    case D:                                                                                                     \
+        CU(cudaFuncSetAttribute(lml_small_kernel<NU, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm))); \
+        lml_small_kernel<NU, D><<<n_prob, FS_THREADS, sm, s>>>(a);                                              \
+        break;
+    switch (DP) {
+        FS_CASE(8)
+        FS_CASE(16)
+        FS_CASE(24)
+        default:
+            CU(cudaFuncSetAttribute(lml_small_kernel<NU, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
+            lml_small_kernel<NU, 32><<<n_prob, FS_THREADS, sm, s>>>(a);
+            break;
+    }
+#undef FS_CASE
+    CU(cudaGetLastError());
+    return AOED_OK;
+}
+
+int launch_lml_small(int nu, int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t s) {
+    switch (nu) {
+        case 1: return launch_lml_small_dp<1>(DP, a, n_prob, s);
+        case 3: return launch_lml_small_dp<3>(DP, a, n_prob, s);
+        case 5: return launch_lml_small_dp<5>(DP, a, n_prob, s);
+        default: return launch_lml_small_dp<-1>(DP, a, n_prob, s);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -580,81 +809,84 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
                       double* h_grad) {
     if (!gp || !h_obj || !h_theta || !h_lml) return fail(AOED_ERR_INVALID, "null argument");
     if (!gp->has_train) return fail(AOED_ERR_INVALID, "set_train must be called first");
+    if (n_prob <= 0) return AOED_OK;
     CU(cudaSetDevice(gp->device));
-    cudaStream_t s = gp->streams[0];
     const int N = gp->N, Npad = gp->Npad, m = gp->m, d = gp->d, p = d + 2, DP = gp->DP;
-    const size_t NN = size_t(Npad) * Npad;
-    cublasSetStream(gp->blas, s);
-    // scratch: slot 0 of the per-objective arrays is reused problem by problem, so a later
-    // set_theta is required before evaluating (has_theta is cleared).
-    gp->has_theta = false;
-    double* Kinv = gp->dLinv;       // scratch
-    double* alpha = gp->dAlpha;     // scratch [Npad]
-    for (int b = 0; b < n_prob; ++b) {
-        const int o = h_obj[b];
-        if (o < 0 || o >= m) return fail(AOED_ERR_INVALID, "objective index out of range");
-        const double* th = h_theta + size_t(b) * p;
-        CHK(upload_theta_slot(gp, 0, th, s));
-        int info = 0;
-        CHK(factor_slot(gp, 0, &info, s));
-        if (info != 0) {  // _gpr.py:589-593
-            h_lml[b] = -std::numeric_limits<double>::infinity();
-            if (h_grad)
-                for (int k = 0; k < p; ++k) h_grad[size_t(b) * p + k] = 0.0;
-            continue;
-        }
-        CU(cudaMemcpyAsync(alpha, gp->dY + size_t(o) * Npad, size_t(Npad) * sizeof(double), cudaMemcpyDeviceToDevice, s));
-        if (cusolverDnDpotrs(gp->solver, CUBLAS_FILL_MODE_UPPER, N, 1, gp->dK, Npad, alpha, Npad, gp->dInfo) !=
-            CUSOLVER_STATUS_SUCCESS)
-            return fail(AOED_ERR_CUDA, "cusolverDnDpotrs failed");
-        std::vector<double> hal(N), hdiag(N);
-        CU(cudaMemcpyAsync(hal.data(), alpha, size_t(N) * sizeof(double), cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpy2DAsync(hdiag.data(), sizeof(double), gp->dK, (size_t(Npad) + 1) * sizeof(double), sizeof(double),
-                             N, cudaMemcpyDeviceToHost, s));
-        if (h_grad) {
-            // K^-1 = solve against the identity (what sklearn does, _gpr.py:631-633)
-            set_identity_kernel<<<dim3((Npad + 127) / 128, Npad, 1), 128, 0, s>>>(Kinv, N, Npad);
-            if (cusolverDnDpotrs(gp->solver, CUBLAS_FILL_MODE_UPPER, N, N, gp->dK, Npad, Kinv, Npad, gp->dInfo) !=
-                CUSOLVER_STATUS_SUCCESS)
-                return fail(AOED_ERR_CUDA, "cusolverDnDpotrs (inverse) failed");
-            LmlGradArgs ga;
-            ga.Ts = gp->dTs; ga.c1c2 = gp->dC1C2; ga.alpha = alpha; ga.Kinv = Kinv; ga.partial = gp->dGradPartial;
-            ga.N = N; ga.Npad = Npad; ga.DP = DP;
-            const int nb = (N + 15) / 16;
-            ga.nBlocksX = nb; ga.nBlocksY = nb;
-            launch_lmlgrad(gp->nu, DP, ga, dim3(nb, nb, 1), s);
-            lml_grad_reduce_kernel<<<1, DP + 2, 0, s>>>(gp->dGradPartial, nb * nb, DP + 2, gp->dGrad);
-            gp->n_launches += 3;
+    for (int b = 0; b < n_prob; ++b)
+        if (h_obj[b] < 0 || h_obj[b] >= m) return fail(AOED_ERR_INVALID, "objective index out of range");
+    CHK(ensure_batch(gp, n_prob));
+    cudaStream_t s0 = gp->streams[0];
+    CU(cudaMemcpyAsync(gp->dThetaB, h_theta, size_t(n_prob) * p * sizeof(double), cudaMemcpyHostToDevice, s0));
+    CU(cudaMemcpyAsync(gp->dObjB, h_obj, size_t(n_prob) * sizeof(int), cudaMemcpyHostToDevice, s0));
+    const bool want_grad = h_grad != nullptr;
+    const char* force = getenv("AOED_FIT_PATH");  // "blocked" forces the large-N path (tests)
+    const bool small = N <= FS_MAX_N && !(force && strcmp(force, "blocked") == 0);
+    if (small) {
+        // one CTA per problem, everything in shared memory
+        LmlSmallArgs a;
+        a.X = gp->dX; a.Y = gp->dY; a.theta = gp->dThetaB; a.obj = gp->dObjB; a.res = gp->dResB;
+        a.N = N; a.Npad = Npad; a.d = d; a.want_grad = want_grad ? 1 : 0;
+        CHK(launch_lml_small(gp->nu, DP, a, n_prob, s0));
+        gp->n_launches++;
+        gp->n_fit_small += n_prob;
+    } else {
+        CHK(ensure_fit_ctx(gp));
+        CU(cudaStreamSynchronize(s0));  // thetas uploaded
+        const int nb = (N + 15) / 16;
+        for (int b = 0; b < n_prob; ++b) {
+            FitCtx& c = gp->fit[b % gp->nfit];
+            cudaStream_t s = c.stream;
+            const int o = h_obj[b];
+            double* res = gp->dResB + size_t(b) * (p + 1);
+            theta_prep_kernel<<<(Npad * DP + 255) / 256, 256, 0, s>>>(gp->dX, gp->dThetaB + size_t(b) * p, N, Npad, d, DP,
+                                                                     c.Ts, c.c1c2);
+            KmatArgs ka;
+            ka.Ts = c.Ts; ka.c1c2 = c.c1c2; ka.K = c.K; ka.N = N; ka.Npad = Npad; ka.DP = DP;
+            launch_kmat(gp->nu, DP, ka, dim3(nb, nb, 1), s);
             CU(cudaGetLastError());
-            std::vector<double> hg(DP + 2);
-            CU(cudaMemcpyAsync(hg.data(), gp->dGrad, (DP + 2) * sizeof(double), cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-            double* g = h_grad + size_t(b) * p;
-            g[0] = hg[0];
-            for (int k = 0; k < d; ++k) g[1 + k] = hg[1 + k];
-            g[d + 1] = hg[DP + 1];
-        } else {
-            CU(cudaStreamSynchronize(s));
+            // row-major lower L  <=>  column-major upper U = L^T with K = U^T U
+            if (cusolverDnDpotrf(c.solver, CUBLAS_FILL_MODE_UPPER, N, c.K, Npad, c.work, c.lwork, c.info) !=
+                CUSOLVER_STATUS_SUCCESS)
+                return fail(AOED_ERR_CUDA, "cusolverDnDpotrf failed");
+            CU(cudaMemcpyAsync(c.alpha, gp->dY + size_t(o) * Npad, size_t(Npad) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            if (cusolverDnDpotrs(c.solver, CUBLAS_FILL_MODE_UPPER, N, 1, c.K, Npad, c.alpha, Npad, c.info + 1) !=
+                CUSOLVER_STATUS_SUCCESS)
+                return fail(AOED_ERR_CUDA, "cusolverDnDpotrs failed");
+            lml_value_kernel<<<1, 256, 0, s>>>(gp->dY + size_t(o) * Npad, c.alpha, c.K, N, Npad, c.info, res);
+            gp->n_launches += 3;
+            if (want_grad) {
+                // K^-1 from the factor in place (N^3 2/3 flops instead of sklearn's cho_solve against I, _gpr.py:631-633)
+                if (cusolverDnDpotri(c.solver, CUBLAS_FILL_MODE_UPPER, N, c.K, Npad, c.work, c.lwork, c.info + 1) !=
+                    CUSOLVER_STATUS_SUCCESS)
+                    return fail(AOED_ERR_CUDA, "cusolverDnDpotri failed");
+                LmlGradArgs ga;
+                ga.Ts = c.Ts; ga.c1c2 = c.c1c2; ga.alpha = c.alpha; ga.Kinv = c.K; ga.partial = c.partial;
+                ga.N = N; ga.Npad = Npad; ga.DP = DP; ga.nBlocksX = nb; ga.nBlocksY = nb;
+                launch_lmlgrad(gp->nu, DP, ga, dim3(nb, nb, 1), s);
+                lml_grad_reduce_kernel<<<DP + 2, 256, 0, s>>>(c.partial, nb * nb, DP, d, c.info, res);
+                gp->n_launches += 2;
+            }
+            CU(cudaGetLastError());
         }
-        double quad = 0.0, logdet = 0.0;
-        for (int i = 0; i < N; ++i) {
-            quad += gp->Yn[size_t(i) * m + o] * hal[i];
-            logdet += log(hdiag[i]);
-        }
-        h_lml[b] = -0.5 * quad - logdet - 0.5 * N * log(2.0 * M_PI);
+        for (int i = 0; i < gp->nfit; ++i) CU(cudaStreamSynchronize(gp->fit[i].stream));
+        gp->n_fit_blocked += n_prob;
     }
-    (void)NN;
+    std::vector<double> res(size_t(n_prob) * (p + 1));
+    CU(cudaMemcpyAsync(res.data(), gp->dResB, res.size() * sizeof(double), cudaMemcpyDeviceToHost, s0));
+    CU(cudaStreamSynchronize(s0));
+    for (int b = 0; b < n_prob; ++b) {
+        h_lml[b] = res[size_t(b) * (p + 1)];
+        if (want_grad)
+            for (int k = 0; k < p; ++k) h_grad[size_t(b) * p + k] = res[size_t(b) * (p + 1) + 1 + k];
+    }
     return AOED_OK;
 }
 
 static int eval_common(aoed_gp_t* gp, int64_t n_rows, uint32_t flags, int acq_kind, const double* h_acq_param,
-                       bool& want_std, bool& want_grad, AcqDev& acq, const void* hF, const void* hS) {
+                       bool& want_std, bool& want_grad, AcqDev& acq) {
     if (!gp) return fail(AOED_ERR_INVALID, "null handle");
     if (!gp->has_theta) return fail(AOED_ERR_INVALID, "surrogate model is not fitted yet");
     if (n_rows < 0) return fail(AOED_ERR_INVALID, "negative row count");
-    if (flags & AOED_EVAL_HESS) {
-        if (hF == nullptr && hS == nullptr) {}
-    }
     want_std = (flags & AOED_EVAL_STD) != 0 || acq_kind >= AOED_ACQ_UCB;
     want_grad = (flags & AOED_EVAL_GRAD) != 0;
     CHK(make_acq(gp, acq_kind, flags, h_acq_param, acq));
@@ -666,19 +898,24 @@ int aoed_gp_eval_device(aoed_gp_t* gp, int64_t n_rows, const double* d_Xn, uint3
                         double* d_hF, double* d_hS, double* d_A, double* d_dA, double* d_hA, void* stream) {
     bool want_std, want_grad;
     AcqDev acq;
-    CHK(eval_common(gp, n_rows, flags, acq_kind, h_acq_param, want_std, want_grad, acq, d_hF, d_hS));
-    if (flags & AOED_EVAL_HESS) return fail(AOED_ERR_UNSUPPORTED, "hessian path: use aoed_gp_eval (host API)");
-    (void)d_hF; (void)d_hS; (void)d_hA;
+    CHK(eval_common(gp, n_rows, flags, acq_kind, h_acq_param, want_std, want_grad, acq));
     if (n_rows == 0) return AOED_OK;
     if (!d_Xn) return fail(AOED_ERR_INVALID, "null input");
     CU(cudaSetDevice(gp->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int64_t cap = std::min<int64_t>(chunk_cap(), round_up64(n_rows, 128));
-    CHK(ensure_ws(gp, gp->ws[0], cap, false));
-    Workspace& w = gp->ws[0];
+    const bool hess = (flags & AOED_EVAL_HESS) != 0;
     const int m = gp->m, d = gp->d;
-    for (int64_t r0 = 0; r0 < n_rows; r0 += w.cols) {
-        const int64_t rows = std::min<int64_t>(w.cols, n_rows - r0);
+    Workspace& w = gp->ws[0];
+    int64_t step;
+    if (hess) {
+        step = hess_rows_cap(gp, n_rows);
+        CHK(ensure_ws_hess(gp, w, step, false));
+    } else {
+        CHK(ensure_ws(gp, w, std::min<int64_t>(chunk_cap(), round_up64(n_rows, 128)), false));
+        step = w.cols;
+    }
+    for (int64_t r0 = 0; r0 < n_rows; r0 += step) {
+        const int64_t rows = std::min<int64_t>(step, n_rows - r0);
         EvalOut out;
         out.F = d_F ? d_F + r0 * m : nullptr;
         out.S = d_S ? d_S + r0 * m : nullptr;
@@ -686,7 +923,15 @@ int aoed_gp_eval_device(aoed_gp_t* gp, int64_t n_rows, const double* d_Xn, uint3
         out.dF = d_dF ? d_dF + r0 * m * d : nullptr;
         out.dS = d_dS ? d_dS + r0 * m * d : nullptr;
         out.dA = d_dA ? d_dA + r0 * m * d : nullptr;
-        CHK(eval_chunk(gp, w, d_Xn + r0 * d, rows, want_std, want_grad, acq, out, s));
+        if (hess) {
+            HessOut ho;
+            ho.hF = d_hF ? d_hF + r0 * m * d * d : nullptr;
+            ho.hS = d_hS ? d_hS + r0 * m * d * d : nullptr;
+            ho.hA = d_hA ? d_hA + r0 * m * d * d : nullptr;
+            CHK(eval_hess_chunk(gp, w, d_Xn + r0 * d, rows, want_std, acq, out, ho, s));
+        } else {
+            CHK(eval_chunk(gp, w, d_Xn + r0 * d, rows, want_std, want_grad, acq, out, s));
+        }
     }
     return AOED_OK;
 }
@@ -696,16 +941,23 @@ int aoed_gp_eval(aoed_gp_t* gp, int64_t n_rows, const double* h_Xn, uint32_t fla
                  double* h_hS, double* h_A, double* h_dA, double* h_hA) {
     bool want_std, want_grad;
     AcqDev acq;
-    CHK(eval_common(gp, n_rows, flags, acq_kind, h_acq_param, want_std, want_grad, acq, h_hF, h_hS));
-    if (flags & AOED_EVAL_HESS) return fail(AOED_ERR_UNSUPPORTED, "hessian kernels not built yet");
-    (void)h_hF; (void)h_hS; (void)h_hA;
+    CHK(eval_common(gp, n_rows, flags, acq_kind, h_acq_param, want_std, want_grad, acq));
     if (n_rows == 0) return AOED_OK;
     if (!h_Xn) return fail(AOED_ERR_INVALID, "null input");
     CU(cudaSetDevice(gp->device));
     const int m = gp->m, d = gp->d;
-    const int64_t cap = std::min<int64_t>(chunk_cap(), round_up64(n_rows, 128));
-    const int nslots = (n_rows > cap) ? 2 : 1;
-    for (int i = 0; i < nslots; ++i) CHK(ensure_ws(gp, gp->ws[i], cap, true));
+    const bool hess = (flags & AOED_EVAL_HESS) != 0;
+    int64_t cap;
+    int nslots;
+    if (hess) {
+        cap = hess_rows_cap(gp, n_rows);
+        nslots = (n_rows > cap) ? 2 : 1;
+        for (int i = 0; i < nslots; ++i) CHK(ensure_ws_hess(gp, gp->ws[i], cap, true));
+    } else {
+        cap = std::min<int64_t>(chunk_cap(), round_up64(n_rows, 128));
+        nslots = (n_rows > cap) ? 2 : 1;
+        for (int i = 0; i < nslots; ++i) CHK(ensure_ws(gp, gp->ws[i], cap, true));
+    }
     int slot = 0;
     for (int64_t r0 = 0; r0 < n_rows; r0 += cap, slot ^= 1) {
         Workspace& w = gp->ws[slot];
@@ -715,21 +967,33 @@ int aoed_gp_eval(aoed_gp_t* gp, int64_t n_rows, const double* h_Xn, uint32_t fla
         CU(cudaStreamSynchronize(s));
         memcpy(w.hX, h_Xn + r0 * d, size_t(rows) * d * sizeof(double));
         CU(cudaMemcpyAsync(w.Xc, w.hX, size_t(rows) * d * sizeof(double), cudaMemcpyHostToDevice, s));
+        const bool grad_out = want_grad;  // gradients are computed internally on the Hessian path either way
         EvalOut out;
         out.F = h_F ? w.oF : nullptr;
         out.S = (h_S && want_std) ? w.oS : nullptr;
         out.A = h_A ? w.oA : nullptr;
-        out.dF = (h_dF && want_grad) ? w.odF : nullptr;
-        out.dS = (h_dS && want_grad && want_std) ? w.odS : nullptr;
-        out.dA = (h_dA && want_grad) ? w.odA : nullptr;
-        CHK(eval_chunk(gp, w, w.Xc, rows, want_std, want_grad, acq, out, s));
-        const size_t b1 = size_t(rows) * m * sizeof(double), b2 = b1 * d;
+        out.dF = (h_dF && grad_out) ? w.odF : nullptr;
+        out.dS = (h_dS && grad_out && want_std) ? w.odS : nullptr;
+        out.dA = (h_dA && grad_out) ? w.odA : nullptr;
+        HessOut ho{nullptr, nullptr, nullptr};
+        if (hess) {
+            ho.hF = h_hF ? w.ohF : nullptr;
+            ho.hS = (h_hS && want_std) ? w.ohS : nullptr;
+            ho.hA = (h_hA && acq.kind != AOED_ACQ_NONE) ? w.ohA : nullptr;
+            CHK(eval_hess_chunk(gp, w, w.Xc, rows, want_std, acq, out, ho, s));
+        } else {
+            CHK(eval_chunk(gp, w, w.Xc, rows, want_std, want_grad, acq, out, s));
+        }
+        const size_t b1 = size_t(rows) * m * sizeof(double), b2 = b1 * d, b3 = b2 * d;
         if (out.F) CU(cudaMemcpyAsync(h_F + r0 * m, w.oF, b1, cudaMemcpyDeviceToHost, s));
         if (out.S) CU(cudaMemcpyAsync(h_S + r0 * m, w.oS, b1, cudaMemcpyDeviceToHost, s));
         if (out.A) CU(cudaMemcpyAsync(h_A + r0 * m, w.oA, b1, cudaMemcpyDeviceToHost, s));
         if (out.dF) CU(cudaMemcpyAsync(h_dF + r0 * m * d, w.odF, b2, cudaMemcpyDeviceToHost, s));
         if (out.dS) CU(cudaMemcpyAsync(h_dS + r0 * m * d, w.odS, b2, cudaMemcpyDeviceToHost, s));
         if (out.dA) CU(cudaMemcpyAsync(h_dA + r0 * m * d, w.odA, b2, cudaMemcpyDeviceToHost, s));
+        if (ho.hF) CU(cudaMemcpyAsync(h_hF + r0 * m * d * d, w.ohF, b3, cudaMemcpyDeviceToHost, s));
+        if (ho.hS) CU(cudaMemcpyAsync(h_hS + r0 * m * d * d, w.ohS, b3, cudaMemcpyDeviceToHost, s));
+        if (ho.hA) CU(cudaMemcpyAsync(h_hA + r0 * m * d * d, w.ohA, b3, cudaMemcpyDeviceToHost, s));
     }
     CU(cudaStreamSynchronize(gp->streams[0]));
     CU(cudaStreamSynchronize(gp->streams[1]));
@@ -749,6 +1013,13 @@ int aoed_gp_get_counters(aoed_gp_t* gp, int64_t* n_launches, double* trmm_ms, in
     if (trmm_ms) *trmm_ms = gp->trmm_ms;
     if (trmm_launches) *trmm_launches = gp->trmm_launches;
     if (trmm_flops) *trmm_flops = gp->trmm_flops;
+    return AOED_OK;
+}
+
+int aoed_gp_get_fit_counters(aoed_gp_t* gp, int64_t* n_small, int64_t* n_blocked) {
+    if (!gp) return fail(AOED_ERR_INVALID, "null handle");
+    if (n_small) *n_small = gp->n_fit_small;
+    if (n_blocked) *n_blocked = gp->n_fit_blocked;
     return AOED_OK;
 }
 

@@ -372,6 +372,12 @@ class GaussianProcess(SurrogateModel):
         _lib.check(lib.aoed_gp_get_counters(h, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(nt), ctypes.byref(fl)))
         return {'launches': n.value, 'trmm_ms': ms.value, 'trmm_launches': nt.value, 'trmm_flops': fl.value}
 
+    def fit_counters(self):
+        lib, h = _lib.load(), self._ensure_handle()
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(lib.aoed_gp_get_fit_counters(h, ctypes.byref(a), ctypes.byref(b)))
+        return {'small': a.value, 'blocked': b.value}
+
     def reset_counters(self):
         _lib.check(_lib.load().aoed_gp_reset_counters(self._ensure_handle()))
 

@@ -100,7 +100,9 @@ int aoed_gp_eval(aoed_gp_t* gp, int64_t n_rows, const double* h_Xn, uint32_t fla
                  double* h_hF, double* h_hS, double* h_A, double* h_dA, double* h_hA);
 
 /* same computation with DEVICE-resident input and outputs (no PCIe traffic), enqueued on `stream`
- * (a cudaStream_t; NULL = default stream).  Used by bench.py's `value` leg and by multi-GPU sharding. */
+ * (a cudaStream_t; NULL = default stream).  Used by bench.py's `value` leg and by multi-GPU sharding.
+ * With AOED_EVAL_HESS the first-order quantities are always computed internally (the variance Hessian and the
+ * EI / PI Hessians need them, gp.py:236-241), whatever AOED_EVAL_GRAD says. */
 int aoed_gp_eval_device(aoed_gp_t* gp, int64_t n_rows, const double* d_Xn, uint32_t flags, int acq_kind,
                         const double* h_acq_param, double* d_F, double* d_S, double* d_dF, double* d_dS,
                         double* d_hF, double* d_hS, double* d_A, double* d_dA, double* d_hA, void* stream);
@@ -111,6 +113,9 @@ int aoed_gp_set_profiling(aoed_gp_t* gp, int on);
 int aoed_gp_get_counters(aoed_gp_t* gp, int64_t* n_launches, double* trmm_ms, int64_t* trmm_launches,
                          double* trmm_flops);
 int aoed_gp_reset_counters(aoed_gp_t* gp);
+/* how many log-marginal-likelihood problems each device path served: the one-CTA-per-problem shared-memory kernel
+ * (n_train <= 232) and the blocked multi-stream path. */
+int aoed_gp_get_fit_counters(aoed_gp_t* gp, int64_t* n_small, int64_t* n_blocked);
 
 /* ---- multi-objective selection ------------------------------------------------------------------
  * replaces find_pareto_front / check_pareto (autooed/utils/pareto.py:27-62): non-dominated mask of Y (n x m),

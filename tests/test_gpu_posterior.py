@@ -194,3 +194,113 @@ def test_error_behaviour():
         gp.evaluate(X[0])  # 1-D input is illegal at the surrogate level
     out = gp.evaluate(np.empty((0, 3)), std=True, gradient=True)
     assert out["F"].shape == (0, 2) and out["dS"].shape == (0, 2, 3)
+
+
+# ---- second derivatives (gp.py:209-242, ucb.py:44-51, ei.py:48-68, pi.py:47-62) -------------------------------------
+@pytest.mark.parametrize("name", FILES)
+def test_mean_hessian_batched_vs_reference(name):
+    """evaluate(std=False, gradient=True, hessian=True) with C > 1 — a valid batched call of the reference."""
+    g = load(name)
+    gp = build(g)
+    out = gp.evaluate(g["Xs"], std=False, gradient=True, hessian=True)
+    assert out["hS"] is None and out["S"] is None
+    tol = cond_tol(g)
+    assert rel(out["F"], g["mean_F"]) < tol
+    assert rel(out["dF"], g["mean_dF"]) < tol
+    assert rel(out["hF"], g["mean_hF"]) < tol
+    # hessian without gradient: same hF, no dF (the reference allows it for the mean)
+    out2 = gp.evaluate(g["Xs"], hessian=True)
+    assert out2["dF"] is None and np.array_equal(out2["hF"], out["hF"])
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_full_hessian_rowstack(name):
+    """std+gradient+hessian: stack of the reference's per-row (C=1) results, literal semantics."""
+    g = load(name)
+    gp = build(g)
+    out = gp.evaluate(g["Xs"], std=True, gradient=True, hessian=True)
+    tol = cond_tol(g)
+    assert rel(out["hF"], g["row_hF"]) < tol
+    orc = oracle_from(g)
+    ref = orc.evaluate(g["Xs"], std=True, gradient=True, hessian=True, mode="literal", var_form="chol")
+    prior = np.exp(g["theta"][:, 0]) + np.exp(g["theta"][:, -1])
+    ok = (((g["row_S"] / g["y_scale"]) ** 2 / prior) > 1e-6).all(axis=1)
+    assert ok.sum() >= 5
+    assert rel(out["hF"], ref["hF"]) < 1e-9
+    # same (triangular) algorithm as the oracle: tight, relative to the largest entry
+    assert rel(out["hS"][ok], ref["hS"][ok]) < 1e-5
+    cond = max(np.linalg.cond(L) ** 2 for L in g["L"])
+    if cond < 1e9:  # where the reference's own explicit-inverse variance keeps its digits (SURVEY.md B-6)
+        assert rel(out["hS"][ok], g["row_hS"][ok]) < 1e-4
+    # std + hessian without gradient: the reference raises UnboundLocalError; here it is the same hS
+    out2 = gp.evaluate(g["Xs"], std=True, hessian=True)
+    assert out2["dS"] is None and np.array_equal(out2["hS"], out["hS"])
+
+
+@pytest.mark.parametrize("name", FILES)
+@pytest.mark.parametrize("kind", ["identity", "ucb", "ei", "pi"])
+@pytest.mark.parametrize("exact", [False, True])
+def test_acquisition_hessian_fused(name, kind, exact):
+    """Fused acquisition Hessian == the oracle's transform applied to the GPU's own surrogate outputs."""
+    import autooed_b200 as ab
+    g = load(name)
+    gp = build(g)
+    cls = {"identity": ab.Identity, "ucb": ab.UpperConfidenceBound, "ei": ab.ExpectedImprovement,
+           "pi": ab.ProbabilityOfImprovement}[kind]
+    acq = cls(gp, exact=exact)
+    acq.fit(g["X"], g["Y"])
+    F, dF, hF = acq.evaluate(g["Xs"], gradient=True, hessian=True)
+    val = gp._evaluate(gp.normalization.do(x=g["Xs"]), True, True, True, exact=exact)
+    oF, odF, ohF = go.acquisition(kind, val, True, True, n_sample=int(g["n_sample"]), y_min=g["y_min"],
+                                  mode="exact" if exact else "literal")
+    fin = np.isfinite(ohF)
+    assert (np.isfinite(hF) == fin).all()
+    assert np.allclose(F, oF, rtol=1e-10, atol=1e-13)
+    assert np.allclose(dF, odF, rtol=1e-9, atol=1e-12)
+    assert np.allclose(hF[fin], ohF[fin], rtol=1e-8, atol=1e-10 * max(1.0, np.abs(ohF[fin]).max()))
+    if not exact and kind in ("identity", "ucb"):
+        cond = max(np.linalg.cond(L) ** 2 for L in g["L"])
+        prior = np.exp(g["theta"][:, 0]) + np.exp(g["theta"][:, -1])
+        ok = (((g["row_S"] / g["y_scale"]) ** 2 / prior) > 1e-6).all(axis=1)
+        if kind == "identity":
+            assert rel(hF, g["acq_identity_hF"]) < cond_tol(g)
+        elif cond < 1e9:
+            assert rel(hF[ok], g["acq_ucb_hF"][ok]) < 1e-4
+
+
+@pytest.mark.parametrize("nu", [1, 3, 5, -1])
+@pytest.mark.parametrize("shape", [(300, 20, 3, 37), (130, 7, 2, 700), (257, 32, 2, 9)])
+def test_exact_hessian_vs_oracle_and_fd(nu, shape, monkeypatch):
+    """`exact` mode: true second derivatives in raw-Y units; multi-chunk (rows*d > chunk) shapes."""
+    from autooed_b200 import GaussianProcess
+    from autooed_b200.problem import SimpleProblem
+    monkeypatch.setenv("AOED_CHUNK", "512")
+    N, d, m, C = shape
+    rng = np.random.default_rng(7 * N + d + nu)
+    X = rng.random((N, d))
+    W = rng.standard_normal((d, m))
+    Y = np.sin(X @ W) + 0.1 * (X ** 2) @ np.abs(W) + 0.05 * rng.standard_normal((N, m))
+    thetas = np.stack([np.concatenate([[rng.uniform(-0.5, 0.5)], rng.uniform(-0.5, 1.0, d), [rng.uniform(-5, -3)]])
+                       for _ in range(m)])
+    Xs = rng.random((C, d))
+    gp = GaussianProcess(SimpleProblem(d, m), nu=nu)
+    gp.fit_fixed(X, Y, thetas)
+    orc = go.GPOracle(d, m, nu=nu).fit(X, Y, thetas=thetas)
+    for mode in ("literal", "exact"):
+        out = gp._evaluate(Xs, True, True, True, exact=(mode == "exact"))
+        ref = orc.evaluate(Xs, std=True, gradient=True, hessian=True, mode=mode, var_form="chol", normalized=True)
+        cond = max(np.linalg.cond(st.L) ** 2 for st in orc.states)
+        tol = max(1e-8, 100 * cond * EPS)
+        assert rel(out["hF"], ref["hF"]) < tol
+        prior = np.exp(thetas[:, 0]) + np.exp(thetas[:, -1])
+        ok = ((ref["S"] / orc.norm.y_scale) ** 2 / prior > 1e-6).all(axis=1)
+        assert rel(out["hS"][ok], ref["hS"][ok]) < max(1e-6, tol * 100)
+    if nu != 1:  # exact mode is the true Hessian: central differences of the GPU gradient (nu=1/2 is not C^2 at data)
+        h = 1e-5
+        out = gp._evaluate(Xs[:4], True, True, True, exact=True)
+        for k in range(min(d, 3)):
+            e = np.zeros(d); e[k] = h
+            op = gp._evaluate(Xs[:4] + e, True, True, False)
+            om = gp._evaluate(Xs[:4] - e, True, True, False)
+            assert np.allclose((op["dF"] - om["dF"]) / (2 * h), out["hF"][:, :, :, k], rtol=1e-4, atol=1e-5 * np.abs(out["hF"]).max())
+            assert np.allclose((op["dS"] - om["dS"]) / (2 * h), out["hS"][:, :, :, k], rtol=1e-3, atol=1e-4 * np.abs(out["hS"]).max())
