@@ -41,6 +41,7 @@ SIGNATURES = {
     "aoed_gp_reset_counters": (ctypes.c_int, [_vp]),
     "aoed_gp_get_fit_counters": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "aoed_pareto_mask": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, _vp, _vp]),
+    "aoed_pareto_mask_rows": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, _vp, ctypes.c_int64, ctypes.c_int64, _vp]),
     "aoed_pareto_rank": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, _vp, _vp]),
     "aoed_hvi_select": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, _vp, ctypes.c_int64, _vp, _vp,
                                        ctypes.c_int, _vp, _vp, _vp]),

@@ -36,15 +36,16 @@ constexpr int MOO_MAX_M = 8;
 // YT: [m][n] objective-major.  alive == nullptr -> all points take part.  dominated[i] = 1 iff some alive j
 // has all(Y_j <= Y_i) and any(Y_j < Y_i)   (utils/pareto.py:39).
 template <int M>
-__global__ void __launch_bounds__(256) dominated_kernel(const double* __restrict__ YT, int64_t n,
-                                                        const uint8_t* __restrict__ alive,
+__global__ void __launch_bounds__(256) dominated_kernel(const double* __restrict__ YT, int64_t n, int64_t row0,
+                                                        int64_t nrows, const uint8_t* __restrict__ alive,
                                                         uint8_t* __restrict__ dominated) {
     __shared__ double tile[M][256];
     __shared__ uint8_t talive[256];
-    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t li = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;  // row of this shard
+    const int64_t i = row0 + li;
     double yi[M];
 #pragma unroll
-    for (int k = 0; k < M; ++k) yi[k] = (i < n) ? YT[k * n + i] : 0.0;
+    for (int k = 0; k < M; ++k) yi[k] = (li < nrows) ? YT[k * n + i] : 0.0;
     bool dom = false;
     for (int64_t j0 = 0; j0 < n; j0 += 256) {
         const int64_t j = j0 + threadIdx.x;
@@ -65,24 +66,28 @@ __global__ void __launch_bounds__(256) dominated_kernel(const double* __restrict
             dom = dom || (le && lt && talive[t]);
         }
     }
-    if (i < n) dominated[i] = dom ? 1 : 0;
+    if (li < nrows) dominated[li] = dom ? 1 : 0;
 }
 
 template <int M>
-void launch_dominated_m(const double* YT, int64_t n, const uint8_t* alive, uint8_t* dom, cudaStream_t s) {
-    dominated_kernel<M><<<unsigned((n + 255) / 256), 256, 0, s>>>(YT, n, alive, dom);
+void launch_dominated_m(const double* YT, int64_t n, int64_t row0, int64_t nrows, const uint8_t* alive, uint8_t* dom,
+                        cudaStream_t s) {
+    dominated_kernel<M><<<unsigned((nrows + 255) / 256), 256, 0, s>>>(YT, n, row0, nrows, alive, dom);
 }
 
-int launch_dominated(int m, const double* YT, int64_t n, const uint8_t* alive, uint8_t* dom, cudaStream_t s) {
+int launch_dominated(int m, const double* YT, int64_t n, const uint8_t* alive, uint8_t* dom, cudaStream_t s,
+                     int64_t row0 = 0, int64_t nrows = -1) {
+    if (nrows < 0) nrows = n;
+    if (nrows == 0) return AOED_OK;
     switch (m) {
-        case 1: launch_dominated_m<1>(YT, n, alive, dom, s); break;
-        case 2: launch_dominated_m<2>(YT, n, alive, dom, s); break;
-        case 3: launch_dominated_m<3>(YT, n, alive, dom, s); break;
-        case 4: launch_dominated_m<4>(YT, n, alive, dom, s); break;
-        case 5: launch_dominated_m<5>(YT, n, alive, dom, s); break;
-        case 6: launch_dominated_m<6>(YT, n, alive, dom, s); break;
-        case 7: launch_dominated_m<7>(YT, n, alive, dom, s); break;
-        case 8: launch_dominated_m<8>(YT, n, alive, dom, s); break;
+        case 1: launch_dominated_m<1>(YT, n, row0, nrows, alive, dom, s); break;
+        case 2: launch_dominated_m<2>(YT, n, row0, nrows, alive, dom, s); break;
+        case 3: launch_dominated_m<3>(YT, n, row0, nrows, alive, dom, s); break;
+        case 4: launch_dominated_m<4>(YT, n, row0, nrows, alive, dom, s); break;
+        case 5: launch_dominated_m<5>(YT, n, row0, nrows, alive, dom, s); break;
+        case 6: launch_dominated_m<6>(YT, n, row0, nrows, alive, dom, s); break;
+        case 7: launch_dominated_m<7>(YT, n, row0, nrows, alive, dom, s); break;
+        case 8: launch_dominated_m<8>(YT, n, row0, nrows, alive, dom, s); break;
         default: return mfail(AOED_ERR_UNSUPPORTED, "n_obj > 8 is not supported");
     }
     MCU(cudaGetLastError());
@@ -292,8 +297,15 @@ std::vector<double> sort_front(const double* front, int64_t k, int m) {
 extern "C" {
 
 int aoed_pareto_mask(int device, int64_t n, int m, const double* h_Y, uint8_t* h_mask) {
-    if (n < 0 || m < 1 || (n > 0 && (!h_Y || !h_mask))) return mfail(AOED_ERR_INVALID, "bad argument");
-    if (n == 0) return AOED_OK;
+    return aoed_pareto_mask_rows(device, n, m, h_Y, 0, n, h_mask);
+}
+
+int aoed_pareto_mask_rows(int device, int64_t n, int m, const double* h_Y, int64_t row_lo, int64_t row_hi,
+                          uint8_t* h_mask) {
+    if (n < 0 || m < 1 || row_lo < 0 || row_hi < row_lo || row_hi > n || (n > 0 && !h_Y) || (row_hi > row_lo && !h_mask))
+        return mfail(AOED_ERR_INVALID, "bad argument");
+    const int64_t nrows = row_hi - row_lo;
+    if (nrows == 0) return AOED_OK;
     if (m > MOO_MAX_M) return mfail(AOED_ERR_UNSUPPORTED, "n_obj > 8 is not supported");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return mfail(AOED_ERR_NO_DEVICE, "no CUDA device");
@@ -301,12 +313,12 @@ int aoed_pareto_mask(int device, int64_t n, int m, const double* h_Y, uint8_t* h
     std::vector<double> yt = to_objective_major(h_Y, n, m);
     Buf dY, dDom;
     MCU(cudaMalloc(&dY.p, yt.size() * sizeof(double)));
-    MCU(cudaMalloc(&dDom.p, size_t(n)));
+    MCU(cudaMalloc(&dDom.p, size_t(nrows)));
     MCU(cudaMemcpy(dY.p, yt.data(), yt.size() * sizeof(double), cudaMemcpyHostToDevice));
-    int rc = launch_dominated(m, dY.as<double>(), n, nullptr, dDom.as<uint8_t>(), nullptr);
+    int rc = launch_dominated(m, dY.as<double>(), n, nullptr, dDom.as<uint8_t>(), nullptr, row_lo, nrows);
     if (rc != AOED_OK) return rc;
-    MCU(cudaMemcpy(h_mask, dDom.p, size_t(n), cudaMemcpyDeviceToHost));
-    for (int64_t i = 0; i < n; ++i) h_mask[i] = h_mask[i] ? 0 : 1;
+    MCU(cudaMemcpy(h_mask, dDom.p, size_t(nrows), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < nrows; ++i) h_mask[i] = h_mask[i] ? 0 : 1;
     return AOED_OK;
 }
 

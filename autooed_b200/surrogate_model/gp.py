@@ -197,15 +197,24 @@ class GaussianProcess(SurrogateModel):
         _lib.check(lib.aoed_gp_set_train(h, self._Xn.shape[0], _lib.ptr(self._Xn), _lib.ptr(self._Yn),
                                          _lib.ptr(y_mean), _lib.ptr(y_scale)))
 
-    def _optimize_thetas(self, objectives):
-        """One L-BFGS-B run per (objective, start) exactly as gp.py:94-101 / _gpr.py:299-340, all in lock-step."""
-        d = self.n_var
-        bounds = theta_bounds(d)
-        problems = []  # (objective, theta0)
+    def _make_problems(self, objectives):
+        """(objective, theta0) per L-BFGS-B run: theta0 of gp.py:126-132 first, then `n_restarts` log-uniform starts
+        (sklearn `n_restarts_optimizer`, _gpr.py:322-340)."""
+        bounds = theta_bounds(self.n_var)
+        problems = []
         for o in objectives:
-            problems.append((o, initial_theta(d)))
+            problems.append((o, initial_theta(self.n_var)))
             for _ in range(self.n_restarts):
                 problems.append((o, self._rng.uniform(bounds[:, 0], bounds[:, 1])))
+        return problems
+
+    def _run_problems(self, problems):
+        """One L-BFGS-B run per problem exactly as gp.py:94-101 / _gpr.py:299-340, all in lock-step on the device.
+        Returns [(theta*, -lml*, nfev)] in problem order."""
+        if not problems:
+            self.fit_info = {'n_problems': 0, 'n_batches': 0, 'n_lml_evals': 0, 'nfev': []}
+            return []
+        bounds = theta_bounds(self.n_var)
         obj_of = [p[0] for p in problems]
 
         def evaluate_batch(ids, thetas):
@@ -233,14 +242,22 @@ class GaussianProcess(SurrogateModel):
         for r in results:
             if isinstance(r, BaseException):
                 raise r
-        best = {}
-        for b, (o, _) in enumerate(problems):
-            x, fun, nfev = results[b]
-            if o not in best or fun < best[o][1]:  # sklearn keeps the minimum of -LML (_gpr.py:339-340)
-                best[o] = (x, fun)
         self.fit_info = {'n_problems': len(problems), 'n_batches': pool.n_batches, 'n_lml_evals': pool.n_evals,
                          'nfev': [r[2] for r in results]}
-        return {o: best[o][0] for o in objectives}
+        return results
+
+    @staticmethod
+    def _pick_best(problems, results):
+        """sklearn keeps the minimum of -LML over the starts of an objective (_gpr.py:339-340); first start wins ties."""
+        best = {}
+        for (o, _), (x, fun, _) in zip(problems, results):
+            if o not in best or fun < best[o][1]:
+                best[o] = (x, fun)
+        return {o: v[0] for o, v in best.items()}
+
+    def _optimize_thetas(self, objectives):
+        problems = self._make_problems(objectives)
+        return self._pick_best(problems, self._run_problems(problems))
 
     def _finalize(self, thetas):
         lib, h = _lib.load(), self._ensure_handle()

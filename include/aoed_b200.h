@@ -121,6 +121,10 @@ int aoed_gp_get_fit_counters(aoed_gp_t* gp, int64_t* n_small, int64_t* n_blocked
  * replaces find_pareto_front / check_pareto (autooed/utils/pareto.py:27-62): non-dominated mask of Y (n x m),
  * minimisation; i is kept iff no j has all(Y_j <= Y_i) and any(Y_j < Y_i). */
 int aoed_pareto_mask(int device, int64_t n, int m, const double* h_Y, uint8_t* h_mask);
+/* the same test for the row shard [row_lo, row_hi) against ALL n points (multi-GPU: rows sharded, columns replicated,
+ * SURVEY.md §8e); h_mask has row_hi - row_lo entries. */
+int aoed_pareto_mask_rows(int device, int64_t n, int m, const double* h_Y, int64_t row_lo, int64_t row_hi,
+                          uint8_t* h_mask);
 /* non-dominated sorting rank (0 = first front), pymoo NonDominatedSorting semantics. */
 int aoed_pareto_rank(int device, int64_t n, int m, const double* h_Y, int32_t* h_rank);
 

@@ -136,3 +136,12 @@ def hv_contributions(Y_candidate, front, ref_point):
         lim = np.maximum(front, y) if front.size else np.empty((0, len(y)))
         out[i] = box - hypervolume(lim, ref)
     return out
+
+
+def hv_contributions_by_difference(Y_candidate, front, ref_point):
+    """HV(front u {y}) - HV(front) per candidate — literally what hvi.py:28-34 evaluates (a dominated y gives exactly 0
+    because the non-dominated pre-filter of the hypervolume drops it)."""
+    Yc = np.asarray(Y_candidate, dtype=np.float64)
+    front = np.asarray(front, dtype=np.float64).reshape(-1, Yc.shape[1])
+    base = hypervolume(front, ref_point)
+    return np.array([hypervolume(np.vstack([front, y]), ref_point) - base for y in Yc])
