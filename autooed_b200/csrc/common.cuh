@@ -61,6 +61,20 @@ __device__ __forceinline__ double norm_pdf(double z) { return kInvSqrt2Pi * exp(
 __device__ __forceinline__ double norm_cdf(double z) { return 0.5 * erfc(-z * kInvSqrt2); }
 __device__ __forceinline__ double safe_div(double a, double b) { return b != 0.0 ? a / b : 0.0; }  // utils/operand.py:8-12
 
+// Selects `dev` for the scope of one C-ABI call and restores the caller's current device afterwards (the host process
+// may be a torch program whose current device must not change under its feet).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

@@ -524,7 +524,8 @@ int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu) {
     if (!(nu == 1 || nu == 3 || nu == 5 || nu == -1)) return fail(AOED_ERR_INVALID, "nu must be 1, 3, 5 or -1");
     const int DP = pick_dp(n_var);
     if (DP < 0) return fail(AOED_ERR_UNSUPPORTED, "n_var > 32 is not supported yet");
-    CU(cudaSetDevice(device));
+    DeviceGuard guard_(device);
+    CU(guard_.err);
     aoed_gp* gp = new aoed_gp();
     gp->device = device; gp->d = n_var; gp->m = n_obj; gp->nu = nu; gp->DP = DP;
     CU(cudaStreamCreateWithFlags(&gp->streams[0], cudaStreamNonBlocking));
@@ -539,7 +540,7 @@ int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu) {
 
 int aoed_gp_destroy(aoed_gp_t* gp) {
     if (!gp) return AOED_OK;
-    cudaSetDevice(gp->device);
+    DeviceGuard guard_(gp->device);
     cudaDeviceSynchronize();
     free_model(gp);
     if (gp->solver) cusolverDnDestroy(gp->solver);
@@ -556,7 +557,8 @@ int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const doub
                       const double* h_y_scale) {
     if (!gp || !h_Xn || !h_Yn) return fail(AOED_ERR_INVALID, "null argument");
     if (n_train < 1) return fail(AOED_ERR_INVALID, "n_train must be positive");
-    CU(cudaSetDevice(gp->device));
+    DeviceGuard guard_(gp->device);
+    CU(guard_.err);
     CU(cudaDeviceSynchronize());
     free_model(gp);
     const int N = n_train, d = gp->d, m = gp->m;
@@ -731,7 +733,8 @@ extern "C" {
 int aoed_gp_set_theta(aoed_gp_t* gp, const double* h_theta) {
     if (!gp || !h_theta) return fail(AOED_ERR_INVALID, "null argument");
     if (!gp->has_train) return fail(AOED_ERR_INVALID, "set_train must be called before set_theta");
-    CU(cudaSetDevice(gp->device));
+    DeviceGuard guard_(gp->device);
+    CU(guard_.err);
     cudaStream_t s = gp->streams[0];
     const int N = gp->N, Npad = gp->Npad, m = gp->m, d = gp->d, p = d + 2;
     const size_t NN = size_t(Npad) * Npad;
@@ -794,7 +797,8 @@ int aoed_gp_set_theta(aoed_gp_t* gp, const double* h_theta) {
 int aoed_gp_get_state(aoed_gp_t* gp, int obj, double* h_L, double* h_alpha, double* h_lml) {
     if (!gp || !gp->has_theta) return fail(AOED_ERR_INVALID, "model has no fitted state");
     if (obj < 0 || obj >= gp->m) return fail(AOED_ERR_INVALID, "objective index out of range");
-    CU(cudaSetDevice(gp->device));
+    DeviceGuard guard_(gp->device);
+    CU(guard_.err);
     const int N = gp->N, Npad = gp->Npad;
     if (h_L)
         CU(cudaMemcpy2D(h_L, size_t(N) * sizeof(double), gp->dL + size_t(obj) * Npad * Npad, size_t(Npad) * sizeof(double),
@@ -810,7 +814,8 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
     if (!gp || !h_obj || !h_theta || !h_lml) return fail(AOED_ERR_INVALID, "null argument");
     if (!gp->has_train) return fail(AOED_ERR_INVALID, "set_train must be called first");
     if (n_prob <= 0) return AOED_OK;
-    CU(cudaSetDevice(gp->device));
+    DeviceGuard guard_(gp->device);
+    CU(guard_.err);
     const int N = gp->N, Npad = gp->Npad, m = gp->m, d = gp->d, p = d + 2, DP = gp->DP;
     for (int b = 0; b < n_prob; ++b)
         if (h_obj[b] < 0 || h_obj[b] >= m) return fail(AOED_ERR_INVALID, "objective index out of range");
@@ -901,7 +906,8 @@ int aoed_gp_eval_device(aoed_gp_t* gp, int64_t n_rows, const double* d_Xn, uint3
     CHK(eval_common(gp, n_rows, flags, acq_kind, h_acq_param, want_std, want_grad, acq));
     if (n_rows == 0) return AOED_OK;
     if (!d_Xn) return fail(AOED_ERR_INVALID, "null input");
-    CU(cudaSetDevice(gp->device));
+    DeviceGuard guard_(gp->device);
+    CU(guard_.err);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool hess = (flags & AOED_EVAL_HESS) != 0;
     const int m = gp->m, d = gp->d;
@@ -944,7 +950,8 @@ int aoed_gp_eval(aoed_gp_t* gp, int64_t n_rows, const double* h_Xn, uint32_t fla
     CHK(eval_common(gp, n_rows, flags, acq_kind, h_acq_param, want_std, want_grad, acq));
     if (n_rows == 0) return AOED_OK;
     if (!h_Xn) return fail(AOED_ERR_INVALID, "null input");
-    CU(cudaSetDevice(gp->device));
+    DeviceGuard guard_(gp->device);
+    CU(guard_.err);
     const int m = gp->m, d = gp->d;
     const bool hess = (flags & AOED_EVAL_HESS) != 0;
     int64_t cap;

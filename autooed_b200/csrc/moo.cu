@@ -309,7 +309,8 @@ int aoed_pareto_mask_rows(int device, int64_t n, int m, const double* h_Y, int64
     if (m > MOO_MAX_M) return mfail(AOED_ERR_UNSUPPORTED, "n_obj > 8 is not supported");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return mfail(AOED_ERR_NO_DEVICE, "no CUDA device");
-    MCU(cudaSetDevice(device));
+    aoed::DeviceGuard guard_(device);
+    MCU(guard_.err);
     std::vector<double> yt = to_objective_major(h_Y, n, m);
     Buf dY, dDom;
     MCU(cudaMalloc(&dY.p, yt.size() * sizeof(double)));
@@ -328,7 +329,8 @@ int aoed_pareto_rank(int device, int64_t n, int m, const double* h_Y, int32_t* h
     if (m > MOO_MAX_M) return mfail(AOED_ERR_UNSUPPORTED, "n_obj > 8 is not supported");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return mfail(AOED_ERR_NO_DEVICE, "no CUDA device");
-    MCU(cudaSetDevice(device));
+    aoed::DeviceGuard guard_(device);
+    MCU(guard_.err);
     std::vector<double> yt = to_objective_major(h_Y, n, m);
     Buf dY, dDom, dAlive, dRank, dRem;
     MCU(cudaMalloc(&dY.p, yt.size() * sizeof(double)));
@@ -362,7 +364,8 @@ int aoed_hv_contributions(int device, int64_t n_cand, int m, const double* h_Yc,
     if (n_cand == 0) return AOED_OK;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return mfail(AOED_ERR_NO_DEVICE, "no CUDA device");
-    MCU(cudaSetDevice(device));
+    aoed::DeviceGuard guard_(device);
+    MCU(guard_.err);
     std::vector<double> yt = to_objective_major(h_Yc, n_cand, m);
     std::vector<double> fs = sort_front(h_front, n_front, m);
     Buf dY, dF, dR, dC;
@@ -392,7 +395,8 @@ int aoed_hvi_select(int device, int64_t n_cand, int m, const double* h_Yc, int64
     if (n_cand == 0 || batch == 0) return AOED_OK;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return mfail(AOED_ERR_NO_DEVICE, "no CUDA device");
-    MCU(cudaSetDevice(device));
+    aoed::DeviceGuard guard_(device);
+    MCU(guard_.err);
     std::vector<double> yt = to_objective_major(h_Yc, n_cand, m);
     std::vector<double> front(h_front, h_front + size_t(n_front) * m);
     std::vector<uint8_t> excl(size_t(n_cand), 0);

@@ -115,9 +115,11 @@ def hvi_select_sharded(Y_candidate, Y, batch_size, contrib_fn=None, front_fn=Non
     scores its shard, one (contribution, global index) pair per rank is gathered, the global arg-max (lowest index on
     ties, hvi.py:35-37) is appended to every replica's front.  Returns the same indices as the single-GPU path."""
     if contrib_fn is None or front_fn is None:
+        from functools import partial
         from autooed_b200.utils.pareto import find_pareto_front, hv_contributions
-        contrib_fn = contrib_fn or hv_contributions
-        front_fn = front_fn or find_pareto_front
+        dev = torch.cuda.current_device() if torch.cuda.is_available() else 0  # this rank's GPU
+        contrib_fn = contrib_fn or partial(hv_contributions, device=dev)
+        front_fn = front_fn or partial(find_pareto_front, device=dev)
     ws, rank = world(group)
     Yc = np.ascontiguousarray(Y_candidate, dtype=np.float64)
     Y = np.asarray(Y, dtype=np.float64)

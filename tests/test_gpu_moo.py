@@ -87,3 +87,26 @@ def test_selection_class_pads_and_transforms():
     np.random.seed(0)
     X_next = sel.select(Xc, Yc, X, Y, 5)  # fewer candidates than the batch: padded (selection/base.py:46-50)
     assert X_next.shape == (5, 4)
+
+
+def _pareto_cases():
+    import os
+    from conftest import GOLDEN
+    z = dict(np.load(os.path.join(GOLDEN, "pareto_cases.npz")))
+    return z, sorted({k.split("__")[0] for k in z})
+
+
+@pytest.mark.parametrize("name", _pareto_cases()[1])
+def test_pareto_vs_reference_golden(name):
+    """Bit-exact non-dominated mask / index set against the unmodified reference `utils/pareto.py:27-62`."""
+    from autooed_b200.utils.pareto import check_pareto, find_pareto_front, pareto_rank
+    z, _ = _pareto_cases()
+    Y = z[f"{name}__Y"]
+    kw = {"obj_type": ["min", "max", "min"]} if name == "objtype" else {}
+    assert np.array_equal(check_pareto(Y, **kw), z[f"{name}__mask"])
+    front, idx = find_pareto_front(Y, return_index=True, **kw)
+    assert sorted(idx) == sorted(int(i) for i in z[f"{name}__idx"])
+    ref = z[f"{name}__front"]
+    assert np.array_equal(front[np.lexsort(front.T[::-1])], ref[np.lexsort(ref.T[::-1])])
+    if not kw:
+        assert np.array_equal(pareto_rank(Y) == 0, z[f"{name}__mask"])
