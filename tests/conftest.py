@@ -15,7 +15,8 @@ def pytest_configure(config):
 
 
 def golden_files():
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    """GP / acquisition fixtures (one per problem shape x nu); pareto_cases.npz is the multi-objective fixture."""
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and "_nu" in f)
 
 
 @pytest.fixture(scope="session")

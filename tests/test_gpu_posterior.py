@@ -226,7 +226,7 @@ def test_full_hessian_rowstack(name):
     prior = np.exp(g["theta"][:, 0]) + np.exp(g["theta"][:, -1])
     ok = (((g["row_S"] / g["y_scale"]) ** 2 / prior) > 1e-6).all(axis=1)
     assert ok.sum() >= 2
-    assert rel(out["hF"], ref["hF"]) < 1e-9
+    assert rel(out["hF"], ref["hF"]) < tol  # alpha itself carries cond(K)*eps between two Cholesky implementations
     # same (triangular) algorithm as the oracle: tight, relative to the largest entry
     assert rel(out["hS"][ok], ref["hS"][ok]) < 1e-5
     cond = max(np.linalg.cond(L) ** 2 for L in g["L"])
