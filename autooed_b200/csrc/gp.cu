@@ -18,6 +18,7 @@
 #include "hessian.cuh"
 #include "posterior.cuh"
 #include "trmm.cuh"
+#include "trmm_tma.cuh"
 
 using namespace aoed;
 
@@ -60,6 +61,7 @@ struct Workspace {
     double *Xc = nullptr, *oF = nullptr, *oS = nullptr, *oA = nullptr, *odF = nullptr, *odS = nullptr, *odA = nullptr;
     double* hX = nullptr;  // pinned input staging
     // Hessian path (lazily allocated): |L^-1 dk_i|^2 partials, Gram matrices, internal first-order outputs, staging
+    CUtensorMap mapKsT, mapW;  // TMA views of the two slabs that serve as B operand of the triangular products
     int64_t hrows = 0;
     double *sumsq2 = nullptr, *gram = nullptr, *bF = nullptr, *bS = nullptr, *bdF = nullptr, *bdS = nullptr;
     double *ohF = nullptr, *ohS = nullptr, *ohA = nullptr;
@@ -93,6 +95,12 @@ struct aoed_gp {
     int solverLwork = 0;
     cusolverDnHandle_t solver = nullptr;
     cublasHandle_t blas = nullptr;
+    CUtensorMap mapLinv, mapLinvT;  // TMA views of the cached factors (A operands)
+    int* dTickets = nullptr;        // tile ticket counters of the persistent triangular products
+    int* hDbg = nullptr;            // host-mapped diagnostics of the persistent kernel (AOED_TRMM_DEBUG=1)
+    int ticket_slot = 0;
+    int trmm_variant = 0;           // 0: persistent TMA kernel, 64 / 128: cp.async tiled kernel with that column tile
+    int ssf = PT_SS_PER_TILE;       // sum-of-squares partials per 128-row tile (4 for the TMA kernel, 1 otherwise)
     FitCtx fit[kMaxFitCtx];
     int nfit = 0;
     double *dThetaB = nullptr, *dResB = nullptr;  // batched LML inputs / results
@@ -153,6 +161,8 @@ void free_model(aoed_gp* gp) {
     if (gp->dThetaB) cudaFree(gp->dThetaB);
     if (gp->dResB) cudaFree(gp->dResB);
     if (gp->dObjB) cudaFree(gp->dObjB);
+    if (gp->dTickets) cudaFree(gp->dTickets);
+    gp->dTickets = nullptr;
     gp->dThetaB = gp->dResB = nullptr;
     gp->dObjB = nullptr;
     gp->batchCap = 0;
@@ -166,6 +176,8 @@ int64_t chunk_cap() {
     if (v < 128) v = 128;
     return round_up64(v, 128);
 }
+
+int make_map_2d(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
 int ensure_ws(aoed_gp* gp, Workspace& w, int64_t cols, bool staging) {
     cols = round_up64(cols, 128);
@@ -182,9 +194,13 @@ int ensure_ws(aoed_gp* gp, Workspace& w, int64_t cols, bool staging) {
         CU(cudaMemset(w.Gr, 0, slab));
         CU(cudaMemset(w.W, 0, slab));
         CU(cudaMemset(w.V, 0, slab));
-        CU(cudaMalloc(&w.sumsq, size_t(m) * gp->mTiles * cols * sizeof(double)));
+        CU(cudaMalloc(&w.sumsq, size_t(m) * gp->mTiles * gp->ssf * cols * sizeof(double)));
         CU(cudaMalloc(&w.part, size_t(m) * gp->JS * (2 + DP) * cols * sizeof(double)));
         CU(cudaMalloc(&w.part2, size_t(m) * gp->JS * (1 + DP) * cols * sizeof(double)));
+        if (gp->trmm_variant == 0) {
+            CHK(make_map_2d(&w.mapKsT, w.KsT, int64_t(m) * Npad, cols, cols, TK));
+            CHK(make_map_2d(&w.mapW, w.W, int64_t(m) * Npad, cols, cols, TK));
+        }
         w.cols = cols;
     }
     if (staging && w.Xc == nullptr) {
@@ -275,21 +291,121 @@ void launch_lmlgrad(int nu, int DP, const LmlGradArgs& a, dim3 grid, cudaStream_
     }
 }
 
-int launch_trmm(aoed_gp* gp, bool upper, const TrmmArgs& a, int colTiles, int batch, cudaStream_t s) {
+template <bool UPPER, int TNV>
+int launch_trmm_cfg(const TrmmArgs& a, int colTiles128, int batch, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(trmm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TRMM_SMEM)));
-        CU(cudaFuncSetAttribute(trmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TRMM_SMEM)));
+        CU(cudaFuncSetAttribute(trmm_kernel<UPPER, TNV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(TrmmCfg<TNV>::SMEM)));
         attr_set = true;
     }
     TrmmArgs args = a;
-    args.colTiles = colTiles;
-    dim3 grid(colTiles * batch, a.mTiles, 1);
+    args.colTiles = colTiles128 * (TN / TNV);
+    dim3 grid(args.colTiles * batch, a.mTiles, 1);
+    trmm_kernel<UPPER, TNV><<<grid, TrmmCfg<TNV>::THREADS, TrmmCfg<TNV>::SMEM, s>>>(args);
+    return AOED_OK;
+}
+
+// ---- TMA descriptors ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// row-major FP64 matrix [rows][ld] (cols valid) viewed through boxes of box_rows x 16 columns, 128-byte swizzle
+int make_map_2d(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(AOED_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+    cuuint64_t strides[1] = {cuuint64_t(ld) * sizeof(double)};
+    cuuint32_t box[2] = {16u, cuuint32_t(box_rows)};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AOED_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+    return AOED_OK;
+}
+
+int trmm_variant_from_env() {
+    const char* e = getenv("AOED_TRMM");
+    if (e && strcmp(e, "tile128") == 0) return 128;
+    if (e && strcmp(e, "tile64") == 0) return 64;
+    return 0;
+}
+
+int sm_count(int device) {
+    static int n[64] = {0};
+    if (device < 0 || device >= 64) return 148;
+    if (n[device] == 0) {
+        cudaDeviceProp prop;
+        n[device] = (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ? prop.multiProcessorCount : 148;
+    }
+    return n[device];
+}
+
+template <bool UPPER>
+int launch_trmm_tma(aoed_gp* gp, const CUtensorMap& mapA, const CUtensorMap& mapB, const TrmmArgs& a, int colTiles,
+                    int batch, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(trmm_tma_kernel<UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PT_SMEM)));
+        attr_set = true;
+    }
+    TrmmTmaArgs t;
+    t.Out = a.Out; t.strideOut = a.strideOut; t.ldo = a.ldo;
+    t.sumsq = a.sumsq; t.strideSS = a.strideSS;
+    t.M = a.M; t.Kpad = a.Kpad; t.Npad = gp->Npad; t.mTiles = a.mTiles; t.colTiles = colTiles; t.batch = batch;
+    gp->ticket_slot = (gp->ticket_slot + 1) % 64;
+    t.counter = gp->dTickets + gp->ticket_slot;
+    CU(cudaMemsetAsync(t.counter, 0, sizeof(int), s));
+    static const bool debug = getenv("AOED_TRMM_DEBUG") != nullptr;
+    if (debug && gp->hDbg == nullptr) {
+        CU(cudaHostAlloc(&gp->hDbg, 64 * sizeof(int), cudaHostAllocMapped));
+        memset(gp->hDbg, 0, 64 * sizeof(int));
+    }
+    t.dbg = debug ? gp->hDbg : nullptr;
+    const int tiles = a.mTiles * colTiles * batch;
+    const int grid = std::min(tiles, sm_count(gp->device));
+    trmm_tma_kernel<UPPER><<<grid, PT_THREADS, PT_SMEM, s>>>(mapA, mapB, t);
+    if (debug) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            const int* d = gp->hDbg;
+            return fail(AOED_ERR_CUDA, std::string("trmm_tma_kernel<") + (UPPER ? "U" : "L") + "> failed: " + cudaGetErrorString(e) +
+                                           " dbg where=" + std::to_string(d[0]) + " block=" + std::to_string(d[1]) + " thread=" +
+                                           std::to_string(d[2]) + " it=" + std::to_string(d[3]) + " parity=" + std::to_string(d[4]) +
+                                           " grid=" + std::to_string(grid) + " tiles=" + std::to_string(tiles));
+        }
+    }
+    return AOED_OK;
+}
+
+// `colTiles` counts 128-column groups of the slab; mapB must view the slab passed as a.B
+int launch_trmm(aoed_gp* gp, bool upper, const TrmmArgs& a, const CUtensorMap& mapB, int colTiles, int batch,
+                cudaStream_t s) {
     if (gp->profiling) CU(cudaEventRecord(gp->ev0, s));
-    if (upper)
-        trmm_kernel<true><<<grid, TTHREADS, TRMM_SMEM, s>>>(args);
-    else
-        trmm_kernel<false><<<grid, TTHREADS, TRMM_SMEM, s>>>(args);
+    if (gp->trmm_variant == 0) {
+        if (upper) CHK(launch_trmm_tma<true>(gp, gp->mapLinvT, mapB, a, colTiles, batch, s));
+        else CHK(launch_trmm_tma<false>(gp, gp->mapLinv, mapB, a, colTiles, batch, s));
+    } else if (gp->trmm_variant == 128) {
+        if (upper) CHK((launch_trmm_cfg<true, 128>(a, colTiles, batch, s)));
+        else CHK((launch_trmm_cfg<false, 128>(a, colTiles, batch, s)));
+    } else {
+        if (upper) CHK((launch_trmm_cfg<true, 64>(a, colTiles, batch, s)));
+        else CHK((launch_trmm_cfg<false, 64>(a, colTiles, batch, s)));
+    }
     CU(cudaGetLastError());
     gp->n_launches++;
     gp->trmm_launches++;
@@ -335,13 +451,13 @@ int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool 
         t.A = gp->dLinv; t.strideA = int64_t(Npad) * Npad; t.lda = Npad;
         t.B = w.KsT; t.strideB = slab; t.ldb = ldc;
         t.Out = want_grad ? w.W : nullptr; t.strideOut = slab; t.ldo = ldc;
-        t.sumsq = w.sumsq; t.strideSS = int64_t(gp->mTiles) * ldc;
+        t.sumsq = w.sumsq; t.strideSS = int64_t(gp->mTiles) * gp->ssf * ldc;
         t.M = gp->N; t.Kpad = gp->Kpad; t.mTiles = gp->mTiles;
-        CHK(launch_trmm(gp, false, t, colTiles, m, s));
+        CHK(launch_trmm(gp, false, t, w.mapKsT, colTiles, m, s));
         if (want_grad) {
             TrmmArgs u = t;
             u.A = gp->dLinvT; u.B = w.W; u.Out = w.V; u.sumsq = nullptr;
-            CHK(launch_trmm(gp, true, u, colTiles, m, s));
+            CHK(launch_trmm(gp, true, u, w.mapW, colTiles, m, s));
             GradsumArgs ga;
             ga.V = w.V; ga.Gr = w.Gr; ga.Ts = gp->dTs; ga.part2 = w.part2; ga.strideSlab = slab;
             ga.N = gp->N; ga.Npad = Npad; ga.ldc = ldc; ga.JS = gp->JS; ga.jchunk = gp->jchunk;
@@ -353,7 +469,7 @@ int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool 
     EpilogueArgs e;
     e.XT = w.XT; e.ell = gp->dEll; e.model = gp->dModel; e.part = w.part; e.part2 = w.part2; e.sumsq = w.sumsq;
     e.F = out.F; e.S = out.S; e.dF = out.dF; e.dS = out.dS; e.A = out.A; e.dA = out.dA;
-    e.rows = rows; e.m = m; e.d = gp->d; e.DP = DP; e.ldc = ldc; e.JS = gp->JS; e.mTiles = gp->mTiles;
+    e.rows = rows; e.m = m; e.d = gp->d; e.DP = DP; e.ldc = ldc; e.JS = gp->JS; e.mTiles = gp->mTiles * gp->ssf;
     e.std = want_std; e.grad = want_grad; e.acq = acq;
     epilogue_kernel<<<dim3(unsigned((rows + 127) / 128), m), 128, 0, s>>>(e);
     gp->n_launches++;
@@ -412,7 +528,7 @@ int ensure_ws_hess(aoed_gp* gp, Workspace& w, int64_t hrows, bool staging) {
             *pp = nullptr;
         }
         const size_t r = size_t(hrows);
-        CU(cudaMalloc(&w.sumsq2, m * gp->mTiles * size_t(w.cols) * sizeof(double)));
+        CU(cudaMalloc(&w.sumsq2, m * gp->mTiles * gp->ssf * size_t(w.cols) * sizeof(double)));
         CU(cudaMalloc(&w.gram, m * r * d * d * sizeof(double)));
         CU(cudaMalloc(&w.bF, r * m * sizeof(double)));
         CU(cudaMalloc(&w.bS, r * m * sizeof(double)));
@@ -462,9 +578,9 @@ int eval_hess_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, 
         t.A = gp->dLinv; t.strideA = int64_t(Npad) * Npad; t.lda = Npad;
         t.B = w.KsT; t.strideB = slab; t.ldb = ldc;
         t.Out = exact ? w.W : nullptr; t.strideOut = slab; t.ldo = ldc;
-        t.sumsq = exact ? nullptr : w.sumsq2; t.strideSS = int64_t(gp->mTiles) * ldc;
+        t.sumsq = exact ? nullptr : w.sumsq2; t.strideSS = int64_t(gp->mTiles) * gp->ssf * ldc;
         t.M = gp->N; t.Kpad = gp->Kpad; t.mTiles = gp->mTiles;
-        CHK(launch_trmm(gp, false, t, colTiles, m, s));
+        CHK(launch_trmm(gp, false, t, w.mapKsT, colTiles, m, s));
         if (exact) {
             GramArgs ga;
             ga.W = w.W; ga.G = w.gram; ga.strideSlab = slab; ga.rows = int(rows); ga.d = d; ga.N = gp->N; ga.ldc = ldc;
@@ -479,7 +595,7 @@ int eval_hess_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, 
     h.F = in.F; h.S = in.S; h.dF = in.dF; h.dS = in.dS;
     h.hF = hout.hF; h.hS = want_std ? hout.hS : nullptr; h.hA = hout.hA;
     h.strideSlab = slab; h.rows = int(rows); h.m = m; h.d = d; h.N = gp->N; h.Npad = Npad; h.ldc = ldc; h.ldx = ldc;
-    h.mTiles = gp->mTiles; h.std = want_std ? 1 : 0; h.acq = acq;
+    h.mTiles = gp->mTiles * gp->ssf; h.std = want_std ? 1 : 0; h.acq = acq;
     launch_hess(gp->nu, DP, h, dim3(unsigned(rows), m), s);
     gp->n_launches++;
     CU(cudaGetLastError());
@@ -528,6 +644,8 @@ int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu) {
     CU(guard_.err);
     aoed_gp* gp = new aoed_gp();
     gp->device = device; gp->d = n_var; gp->m = n_obj; gp->nu = nu; gp->DP = DP;
+    gp->trmm_variant = trmm_variant_from_env();
+    gp->ssf = gp->trmm_variant == 0 ? PT_SS_PER_TILE : 1;
     CU(cudaStreamCreateWithFlags(&gp->streams[0], cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&gp->streams[1], cudaStreamNonBlocking));
     CU(cudaEventCreate(&gp->ev0));
@@ -593,6 +711,11 @@ int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const doub
     CU(cudaMalloc(&gp->dLinv, size_t(m) * Np * Np * sizeof(double)));
     CU(cudaMalloc(&gp->dLinvT, size_t(m) * Np * Np * sizeof(double)));
     CU(cudaMalloc(&gp->dL, size_t(m) * Np * Np * sizeof(double)));
+    CU(cudaMalloc(&gp->dTickets, 64 * sizeof(int)));
+    if (gp->trmm_variant == 0) {
+        CHK(make_map_2d(&gp->mapLinv, gp->dLinv, int64_t(m) * Np, Np, Np, TM));
+        CHK(make_map_2d(&gp->mapLinvT, gp->dLinvT, int64_t(m) * Np, Np, Np, TM));
+    }
     CU(cudaMalloc(&gp->dK, Np * Np * sizeof(double)));
     CU(cudaMalloc(&gp->dC1C2, size_t(m) * 2 * sizeof(double)));
     CU(cudaMalloc(&gp->dInfo, sizeof(int)));

@@ -18,15 +18,21 @@
 namespace aoed {
 
 constexpr int TM = 128;
-constexpr int TN = 128;
+constexpr int TN = 128;  // column granularity of the slabs (workspace columns are padded to this)
 constexpr int TK = 16;
 constexpr int TSTAGES = 4;
-constexpr int TTHREADS = 512;
 constexpr int A_LD = 18;
 constexpr int A_STAGE = TM * A_LD;
-constexpr int B_STAGE = TK * TN;
-constexpr int STAGE_DOUBLES = A_STAGE + B_STAGE;
-constexpr size_t TRMM_SMEM = size_t(TSTAGES) * STAGE_DOUBLES * sizeof(double);
+// Two tilings of the same kernel: 128x128 (16 warps, one CTA per SM) and 128x64 (8 warps, two CTAs per SM whose
+// barrier bubbles overlap each other).
+template <int TNV>
+struct TrmmCfg {
+    static constexpr int THREADS = TNV * 4;  // (TM/32) x (TNV/32) warps of 32x32
+    static constexpr int B_STAGE = TK * TNV;
+    static constexpr int STAGE_DOUBLES = A_STAGE + B_STAGE;
+    static constexpr size_t SMEM = size_t(TSTAGES) * STAGE_DOUBLES * sizeof(double);
+    static constexpr int MIN_CTAS = TNV == 128 ? 1 : 2;
+};
 
 struct TrmmArgs {
     const double* A;  // [batch][mTiles*TM][lda]
@@ -46,11 +52,17 @@ struct TrmmArgs {
     int colTiles;
 };
 
-template <bool UPPER>
-__global__ void __launch_bounds__(TTHREADS, 1) trmm_kernel(TrmmArgs p) {
+template <bool UPPER, int TNV>
+__global__ void __launch_bounds__(TrmmCfg<TNV>::THREADS, TrmmCfg<TNV>::MIN_CTAS) trmm_kernel(TrmmArgs p) {
+    using Cfg = TrmmCfg<TNV>;
+    constexpr int TTHREADS = Cfg::THREADS, STAGE_DOUBLES = Cfg::STAGE_DOUBLES, WN = TNV / 32;
+    constexpr int TN = TNV;  // shadows the slab granularity inside the kernel
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
+    // warp -> 32x32 sub-tile.  Warps w and w+4 share an SM sub-partition; the k-range of a row slice inside the diagonal
+    // block grows with wm, so the 8-warp tiling pairs wm with 3-wm on every sub-partition (equal DMMA work per scheduler).
+    const int wm = (WN == 4) ? warp / WN : ((warp < 4) ? warp : 7 - warp);
+    const int wn = (WN == 4) ? warp % WN : (warp >> 2);
     const int g = lane >> 2, q = lane & 3;
     // Work per CTA grows with the k-range of its row tile.  CTAs are dispatched in linear block order, so the row
     // tile is the SLOW grid index, heaviest first: every heavy tile of the launch starts before any light one and the
@@ -65,19 +77,22 @@ __global__ void __launch_bounds__(TTHREADS, 1) trmm_kernel(TrmmArgs p) {
     // k16-steps of the diagonal 128-block this warp can skip (its rows only see zeros there)
     const int diag0 = UPPER ? 0 : mt * (TM / TK);  // first diagonal step (step index)
     const int lda = p.lda, ldb = p.ldb;
+    // row slices entirely in the zero padding of the last row tile (N not a multiple of 128) do no arithmetic
+    const bool rows_live = mt * TM + wm * 32 < p.M;
 
     auto load_stage = [&](int slot, int kt) {
         double* As = smem + slot * STAGE_DOUBLES;
         double* Bs = As + A_STAGE;
         const int k0 = k_begin + kt * TK;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            int row = (tid >> 3) + 64 * i, ch = tid & 7;
+        for (int i = 0; i < TM * 8 / TTHREADS; ++i) {
+            int row = (tid >> 3) + (TTHREADS / 8) * i, ch = tid & 7;
             cp_async16(As + row * A_LD + ch * 2, A + int64_t(row) * lda + k0 + ch * 2, true);
         }
+        constexpr int CPR = TN / 2;  // 16-byte chunks per B row
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            int k = (tid >> 6) + 8 * i, ch = tid & 63;
+        for (int i = 0; i < TK * CPR / TTHREADS; ++i) {
+            int k = tid / CPR + (TTHREADS / CPR) * i, ch = tid % CPR;
             int phys = (((ch >> 1) ^ ((k >> 2) & 3)) << 1) | (ch & 1);
             cp_async16(Bs + k * TN + phys * 2, B + int64_t(k0 + k) * ldb + ch * 2, true);
         }
@@ -105,7 +120,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) trmm_kernel(TrmmArgs p) {
         }
         // triangular skip inside the diagonal block
         const int kd = kt - diag0;  // 0..7 inside the diagonal block
-        bool active = true;
+        bool active = rows_live;
         if (UPPER) {
             if (kd < 2 * wm) active = false;  // rows >= mt*128 + wm*32 need k >= that
         } else {
