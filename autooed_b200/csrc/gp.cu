@@ -81,7 +81,8 @@ constexpr int kMaxFitCtx = 4;
 
 struct aoed_gp {
     int device = 0, d = 0, m = 0, nu = 1, DP = 8;
-    int N = 0, Npad = 0, Kpad = 0, mTiles = 0, JS = 1, jchunk = 0;
+    int N = 0, Npad = 0, Kpad = 0, mTiles = 0, JS = 1, jchunk = 0;  // JS: CAPACITY of the training-index split (partials)
+    int occ_xcov = 2, occ_gradsum = 5;  // resident CTAs per SM of the two thread-per-candidate kernels
     bool has_train = false, has_theta = false;
     std::vector<double> theta, y_mean, y_scale, lml, Xn, Yn;
     // device model state
@@ -217,6 +218,28 @@ int ensure_ws(aoed_gp* gp, Workspace& w, int64_t cols, bool staging) {
     return AOED_OK;
 }
 
+// Training-index split for the thread-per-candidate kernels: the grid is colTiles x JS x m CTAs; pick JS (<= capacity) so
+// that the CTA count fills whole waves of (SMs x resident CTAs) — a 2.6-wave grid runs as 3 waves, a 1.04-wave grid as 2.
+void choose_split(int N, int colTiles, int m, int js_cap, int ctas_per_wave, int& JS, int& jchunk) {
+    double best = -1.0;
+    JS = 1;
+    const int js_max = std::max(1, std::min(js_cap, (N + XC_JT - 1) / XC_JT));
+    for (int js = 1; js <= js_max; ++js) {
+        const int jc = round_up((N + js - 1) / js, XC_JT);
+        const int real = (N + jc - 1) / jc;
+        if (real != js) continue;
+        const double ctas = double(colTiles) * js * m;
+        const double waves = std::ceil(ctas / ctas_per_wave);
+        double eff = ctas / (waves * ctas_per_wave);  // fraction of the last wave's slots that do work
+        if (waves > 1.0) eff = std::min(eff + 0.02 * (waves - 1.0), 1.0);  // more waves amortise a ragged tail
+        if (eff > best + 1e-9) {
+            best = eff;
+            JS = js;
+        }
+    }
+    jchunk = round_up((N + JS - 1) / JS, XC_JT);
+}
+
 template <int NU, int DP>
 void launch_xcov(const XcovArgs& a, dim3 grid, bool grad, cudaStream_t s) {
     if (grad)
@@ -241,6 +264,32 @@ void launch_xcov_any(int nu, int DP, const XcovArgs& a, dim3 grid, bool grad, cu
         case 16: launch_xcov_nu<16>(nu, a, grid, grad, s); break;
         case 24: launch_xcov_nu<24>(nu, a, grid, grad, s); break;
         default: launch_xcov_nu<32>(nu, a, grid, grad, s); break;
+    }
+}
+
+template <typename K>
+int occ_of(K kernel, int threads) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
+template <int DP>
+int occ_xcov_nu(int nu) {
+    switch (nu) {
+        case 1: return occ_of(xcov_kernel<1, DP, true>, XC_THREADS);
+        case 3: return occ_of(xcov_kernel<3, DP, true>, XC_THREADS);
+        case 5: return occ_of(xcov_kernel<5, DP, true>, XC_THREADS);
+        default: return occ_of(xcov_kernel<-1, DP, true>, XC_THREADS);
+    }
+}
+
+void query_occupancy(int nu, int DP, int& occ_xcov, int& occ_gradsum) {
+    switch (DP) {
+        case 8: occ_xcov = occ_xcov_nu<8>(nu); occ_gradsum = occ_of(gradsum_kernel<8>, XC_THREADS); break;
+        case 16: occ_xcov = occ_xcov_nu<16>(nu); occ_gradsum = occ_of(gradsum_kernel<16>, XC_THREADS); break;
+        case 24: occ_xcov = occ_xcov_nu<24>(nu); occ_gradsum = occ_of(gradsum_kernel<24>, XC_THREADS); break;
+        default: occ_xcov = occ_xcov_nu<32>(nu); occ_gradsum = occ_of(gradsum_kernel<32>, XC_THREADS); break;
     }
 }
 
@@ -442,8 +491,11 @@ int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool 
     xa.KsT = want_std ? w.KsT : nullptr;
     xa.Gr = (want_std && want_grad) ? w.Gr : nullptr;
     xa.part = w.part; xa.strideSlab = slab;
-    xa.N = gp->N; xa.Npad = Npad; xa.ldc = ldc; xa.JS = gp->JS; xa.jchunk = gp->jchunk;
-    launch_xcov_any(gp->nu, DP, xa, dim3(colTiles, gp->JS, m), want_grad, s);
+    const int sms = sm_count(gp->device);
+    int JS1, jchunk1, JS2 = 1, jchunk2 = gp->jchunk;
+    choose_split(gp->N, colTiles, m, gp->JS, sms * gp->occ_xcov, JS1, jchunk1);
+    xa.N = gp->N; xa.Npad = Npad; xa.ldc = ldc; xa.JS = JS1; xa.jchunk = jchunk1;
+    launch_xcov_any(gp->nu, DP, xa, dim3(colTiles, JS1, m), want_grad, s);
     gp->n_launches++;
     CU(cudaGetLastError());
     if (want_std) {
@@ -460,8 +512,9 @@ int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool 
             CHK(launch_trmm(gp, true, u, w.mapW, colTiles, m, s));
             GradsumArgs ga;
             ga.V = w.V; ga.Gr = w.Gr; ga.Ts = gp->dTs; ga.part2 = w.part2; ga.strideSlab = slab;
-            ga.N = gp->N; ga.Npad = Npad; ga.ldc = ldc; ga.JS = gp->JS; ga.jchunk = gp->jchunk;
-            launch_gradsum(DP, ga, dim3(colTiles, gp->JS, m), s);
+            choose_split(gp->N, colTiles, m, gp->JS, sms * gp->occ_gradsum, JS2, jchunk2);
+            ga.N = gp->N; ga.Npad = Npad; ga.ldc = ldc; ga.JS = JS2; ga.jchunk = jchunk2;
+            launch_gradsum(DP, ga, dim3(colTiles, JS2, m), s);
             gp->n_launches++;
             CU(cudaGetLastError());
         }
@@ -469,9 +522,9 @@ int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool 
     EpilogueArgs e;
     e.XT = w.XT; e.ell = gp->dEll; e.model = gp->dModel; e.part = w.part; e.part2 = w.part2; e.sumsq = w.sumsq;
     e.F = out.F; e.S = out.S; e.dF = out.dF; e.dS = out.dS; e.A = out.A; e.dA = out.dA;
-    e.rows = rows; e.m = m; e.d = gp->d; e.DP = DP; e.ldc = ldc; e.JS = gp->JS; e.mTiles = gp->mTiles * gp->ssf;
+    e.rows = rows; e.m = m; e.d = gp->d; e.DP = DP; e.ldc = ldc; e.JS = JS1; e.JS2 = JS2; e.mTiles = gp->mTiles * gp->ssf;
     e.std = want_std; e.grad = want_grad; e.acq = acq;
-    epilogue_kernel<<<dim3(unsigned((rows + 127) / 128), m), 128, 0, s>>>(e);
+    epilogue_kernel<<<dim3(unsigned((rows + EPI_THREADS - 1) / EPI_THREADS), m), EPI_THREADS, 0, s>>>(e);
     gp->n_launches++;
     CU(cudaGetLastError());
     return AOED_OK;
@@ -644,6 +697,7 @@ int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu) {
     CU(guard_.err);
     aoed_gp* gp = new aoed_gp();
     gp->device = device; gp->d = n_var; gp->m = n_obj; gp->nu = nu; gp->DP = DP;
+    query_occupancy(nu, DP, gp->occ_xcov, gp->occ_gradsum);
     gp->trmm_variant = trmm_variant_from_env();
     gp->ssf = gp->trmm_variant == 0 ? PT_SS_PER_TILE : 1;
     CU(cudaStreamCreateWithFlags(&gp->streams[0], cudaStreamNonBlocking));
@@ -684,7 +738,7 @@ int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const doub
     gp->Npad = round_up(N, TM);
     gp->Kpad = round_up(N, TK);
     gp->mTiles = gp->Npad / TM;
-    gp->JS = std::min(16, std::max(1, (N + 255) / 256));
+    gp->JS = std::min(16, std::max(1, (N + XC_JT - 1) / XC_JT));  // capacity; the split per launch is choose_split()
     gp->jchunk = round_up((N + gp->JS - 1) / gp->JS, XC_JT);
     gp->JS = (N + gp->jchunk - 1) / gp->jchunk;
     gp->has_train = true;

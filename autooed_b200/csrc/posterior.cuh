@@ -70,32 +70,53 @@ __global__ void __launch_bounds__(XC_THREADS) xcov_kernel(XcovArgs p) {
         for (int i = tid; i < nj * DP; i += XC_THREADS) (&ts[0][0])[i] = Ts[int64_t(j0) * DP + i];
         if (tid < nj) al[tid] = alpha[j0 + tid];
         __syncthreads();
-        for (int jj = 0; jj < nj; ++jj) {
-            double r2 = 0.0;
+        // two training points per iteration with split distance accumulators: the serial FMA -> sqrt -> exp chains of
+        // independent points overlap (the kernel is FP64-latency bound at 4-8 warps per SM)
+        for (int jj = 0; jj < nj; jj += 2) {
+            const bool two = jj + 1 < nj;
+            const int j1 = two ? jj + 1 : jj;
+            double ra0 = 0.0, ra1 = 0.0, rb0 = 0.0, rb1 = 0.0;
 #pragma unroll
             for (int k = 0; k < DP; k += 2) {
-                double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
-                double d0 = xs[k] - t.x, d1 = xs[k + 1] - t.y;
-                r2 = fma(d0, d0, r2);
-                r2 = fma(d1, d1, r2);
+                const double2 ta = *reinterpret_cast<const double2*>(&ts[jj][k]);
+                const double2 tb = *reinterpret_cast<const double2*>(&ts[j1][k]);
+                const double a0 = xs[k] - ta.x, a1 = xs[k + 1] - ta.y;
+                const double b0 = xs[k] - tb.x, b1 = xs[k + 1] - tb.y;
+                ra0 = fma(a0, a0, ra0);
+                ra1 = fma(a1, a1, ra1);
+                rb0 = fma(b0, b0, rb0);
+                rb1 = fma(b1, b1, rb1);
             }
-            const double r = sqrt(r2);
-            double phi, gor;
-            kernel_profile<NU>(r, r2, phi, gor);
-            const double kv = fma(c1, phi, c2);
-            const double a = al[jj];
-            mu = fma(kv, a, mu);
-            if (KsT) KsT[int64_t(j0 + jj) * p.ldc + c] = kv;
+            const double r2a = ra0 + ra1, r2b = rb0 + rb1;
+            const double ra = sqrt(r2a), rb = sqrt(r2b);
+            double phia, gora, phib, gorb;
+            kernel_profile<NU>(ra, r2a, phia, gora);
+            kernel_profile<NU>(rb, r2b, phib, gorb);
+            const double kva = fma(c1, phia, c2), kvb = fma(c1, phib, c2);
+            const double aa = al[jj], ab = two ? al[j1] : 0.0;
+            mu = fma(kva, aa, mu);
+            mu = fma(kvb, ab, mu);
+            if (KsT) {
+                KsT[int64_t(j0 + jj) * p.ldc + c] = kva;
+                if (two) KsT[int64_t(j0 + j1) * p.ldc + c] = kvb;
+            }
             if (GRAD) {
-                const double w = c1 * gor;
-                if (Gr) Gr[int64_t(j0 + jj) * p.ldc + c] = w;
-                const double wa = w * a;
-                s0 += wa;
+                const double wa = c1 * gora, wb = c1 * gorb;
+                if (Gr) {
+                    Gr[int64_t(j0 + jj) * p.ldc + c] = wa;
+                    if (two) Gr[int64_t(j0 + j1) * p.ldc + c] = wb;
+                }
+                const double waa = wa * aa, wab = wb * ab;
+                s0 += waa;
+                s0 += wab;
 #pragma unroll
                 for (int k = 0; k < DP; k += 2) {
-                    double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
-                    sk[k] = fma(wa, t.x, sk[k]);
-                    sk[k + 1] = fma(wa, t.y, sk[k + 1]);
+                    const double2 ta = *reinterpret_cast<const double2*>(&ts[jj][k]);
+                    const double2 tb = *reinterpret_cast<const double2*>(&ts[j1][k]);
+                    sk[k] = fma(waa, ta.x, sk[k]);
+                    sk[k + 1] = fma(waa, ta.y, sk[k + 1]);
+                    sk[k] = fma(wab, tb.x, sk[k]);
+                    sk[k + 1] = fma(wab, tb.y, sk[k + 1]);
                 }
             }
         }
@@ -179,7 +200,7 @@ struct EpilogueArgs {
     const double* sumsq;  // [m][mTiles][ldc]
     double *F, *S, *dF, *dS, *A, *dA;  // outputs for rows [0, rows): (rows, m) / (rows, m, d); any may be null
     int64_t rows;
-    int m, d, DP, ldc, JS, mTiles;
+    int m, d, DP, ldc, JS, JS2, mTiles;  // JS / JS2: training-index splits of xcov_kernel / gradsum_kernel
     int std, grad;
     AcqDev acq;
 };
@@ -214,7 +235,9 @@ __device__ __forceinline__ void acq_first_order(const AcqDev& acq, int o, double
     }
 }
 
-__global__ void __launch_bounds__(128) epilogue_kernel(EpilogueArgs p) {
+constexpr int EPI_THREADS = 64;  // small CTAs: the grid is only rows/64 x m, spread it over all SMs
+
+__global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(EpilogueArgs p) {
     const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     const int o = blockIdx.y;
     if (c >= p.rows) return;
@@ -223,11 +246,13 @@ __global__ void __launch_bounds__(128) epilogue_kernel(EpilogueArgs p) {
     const int64_t pstride = int64_t(2 + DP) * ldc;
     const double* part = p.part + int64_t(o) * p.JS * pstride + c;
     double mu = 0.0;
+#pragma unroll 4
     for (int js = 0; js < p.JS; ++js) mu += part[js * pstride];
     double sd = 0.0;
     if (p.std) {
         double acc = 0.0;
         const double* ss = p.sumsq + int64_t(o) * p.mTiles * ldc + c;
+#pragma unroll 8
         for (int t = 0; t < p.mTiles; ++t) acc += ss[int64_t(t) * ldc];
         double var = (md.c1 + md.c2) - acc;  // kernel_.diag(X) - |L^-1 k*|^2   (gp.py:159-161)
         if (var < 0.0) var = 0.0;            // gp.py:163-165
@@ -245,22 +270,27 @@ __global__ void __launch_bounds__(128) epilogue_kernel(EpilogueArgs p) {
     }
     if (!p.grad) return;
     double s0 = 0.0, t0 = 0.0;
+#pragma unroll 4
     for (int js = 0; js < p.JS; ++js) s0 += part[js * pstride + ldc];
     const int64_t p2stride = int64_t(1 + DP) * ldc;
-    const double* part2 = p.part2 + int64_t(o) * p.JS * p2stride + c;
-    if (p.std)
-        for (int js = 0; js < p.JS; ++js) t0 += part2[js * p2stride];
+    const double* part2 = p.part2 + int64_t(o) * p.JS2 * p2stride + c;
+    if (p.std) {
+#pragma unroll 4
+        for (int js = 0; js < p.JS2; ++js) t0 += part2[js * p2stride];
+    }
     for (int k = 0; k < p.d; ++k) {
         const double ell = p.ell[o * DP + k];
         const double xs = p.XT[int64_t(k) * ldc + c] / ell;
         double sk = 0.0;
+#pragma unroll 4
         for (int js = 0; js < p.JS; ++js) sk += part[js * pstride + int64_t(2 + k) * ldc];
         const double dmu = (s0 * xs - sk) / ell;  // gp.py:196 via SURVEY.md A-4
         const double dFk = dmu * md.y_scale;      // base.py:107
         double dSk = 0.0;
         if (p.std) {
             double tk = 0.0;
-            for (int js = 0; js < p.JS; ++js) tk += part2[js * p2stride + int64_t(1 + k) * ldc];
+#pragma unroll 4
+            for (int js = 0; js < p.JS2; ++js) tk += part2[js * p2stride + int64_t(1 + k) * ldc];
             const double dvar = -2.0 * (t0 * xs - tk) / ell;  // gp.py:201-205
             dSk = 0.5 * safe_div(dvar, sd) * md.y_scale;      // gp.py:206, base.py:109
         }

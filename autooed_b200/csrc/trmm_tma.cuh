@@ -88,6 +88,27 @@ struct TrmmTmaArgs {
     int* dbg;         // host-mapped diagnostics (who timed out where), or nullptr
 };
 
+constexpr int PT_COL_GROUP = 8;  // column tiles whose B panels (all batches) are meant to stay L2-resident together
+
+// Ticket -> tile.  Order: groups of PT_COL_GROUP column tiles outermost (their B panels, 8*128 columns x Npad x batch
+// = 50 MB at N = 2048, m = 3, stay in the 126 MB L2 while every row tile of the group streams over them), inside a group
+// heaviest row tiles first, then batch, then column tile (CTAs running concurrently share the A panel of one row tile).
+template <bool UPPER>
+__device__ __forceinline__ void decode_tile(int t, int mTiles, int colTiles, int batch, int& mt, int& b, int& ct) {
+    const int full = PT_COL_GROUP * batch * mTiles;
+    const int ng = (colTiles + PT_COL_GROUP - 1) / PT_COL_GROUP;
+    int grp = t / full, r = t - grp * full, gsz = PT_COL_GROUP;
+    if (grp >= ng - 1) {
+        grp = ng - 1;
+        r = t - grp * full;
+        gsz = colTiles - grp * PT_COL_GROUP;
+    }
+    const int mr = r / (gsz * batch), rem = r - mr * (gsz * batch);
+    mt = UPPER ? mr : mTiles - 1 - mr;
+    b = rem / gsz;
+    ct = grp * PT_COL_GROUP + (rem - b * gsz);
+}
+
 template <bool UPPER>
 __global__ void __launch_bounds__(PT_THREADS, 1)
 trmm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TrmmTmaArgs p) {
@@ -98,7 +119,6 @@ trmm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     volatile int* stage_tile = reinterpret_cast<volatile int*>(gen + PT_STAGES * PT_STAGE_BYTES + 2 * PT_STAGES * 8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = p.mTiles * p.colTiles * p.batch;
-    const int per_mt = p.colTiles * p.batch;
 
     if (tid == 0) {
         for (int s = 0; s < PT_STAGES; ++s) {
@@ -124,9 +144,8 @@ trmm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 mbar_arrive(bars + 8 * s);
                 return;
             }
-            const int mr = tile / per_mt, rem = tile % per_mt;
-            const int mt = UPPER ? mr : p.mTiles - 1 - mr;  // heaviest row tiles first
-            const int b = rem / p.colTiles, ct = rem % p.colTiles;
+            int mt, b, ct;
+            decode_tile<UPPER>(tile, p.mTiles, p.colTiles, p.batch, mt, b, ct);
             const int k_begin = UPPER ? mt * TM : 0;
             const int k_end = UPPER ? p.Kpad : min(p.Kpad, (mt + 1) * TM);
             const int KT = (k_end - k_begin) / TK;
@@ -168,9 +187,8 @@ trmm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         const int tile = stage_tile[it % PT_STAGES];
         if (tile < 0) break;
-        const int mr = tile / per_mt, rem = tile % per_mt;
-        const int mt = UPPER ? mr : p.mTiles - 1 - mr;
-        const int b = rem / p.colTiles, ct = rem % p.colTiles;
+        int mt, b, ct;
+        decode_tile<UPPER>(tile, p.mTiles, p.colTiles, p.batch, mt, b, ct);
         const int k_begin = UPPER ? mt * TM : 0;
         const int k_end = UPPER ? p.Kpad : min(p.Kpad, (mt + 1) * TM);
         const int KT = (k_end - k_begin) / TK;

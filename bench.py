@@ -233,8 +233,21 @@ def run_ours(args):
         achieved = cnt["trmm_flops"] / (cnt["trmm_ms"] * 1e-3) * 1e-12
         peak = dgemm_peak(torch, dev)
         step_ms_profiled = cnt["trmm_ms"]
-        roofline = {"bound": "tensor", "kernel": "trmm_kernel (FP64 DMMA m8n8k4 triangular product)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        variant = os.environ.get("AOED_TRMM", "tma")
+        kname = {"tma": "trmm_tma_kernel (persistent TMA + mbarrier ring + FP64 DMMA m8n8k4 triangular product)",
+                 "tile64": "trmm_kernel<.,64> (cp.async 128x64 tiles, FP64 DMMA m8n8k4 triangular product)",
+                 "tile128": "trmm_kernel<.,128> (cp.async 128x128 tiles, FP64 DMMA m8n8k4 triangular product)"}.get(variant, variant)
+        traffic, traffic_src = None, None
+        prof = os.path.join(ROOT, "profiles", "ncu_trmm_summary.json")
+        if variant == "tma" and os.path.exists(prof):  # dram bytes per launch from the committed `ncu --set full` capture
+            ks = [k for k in json.load(open(prof))["kernels"] if "trmm_tma" in k["kernel"] and "dram_traffic_bytes" in k]
+            if ks:
+                traffic = sum(k["dram_traffic_bytes"] for k in ks) / len(ks)
+                traffic_src = "profiles/ncu_trmm_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, mean of the LOWER and UPPER launch)"
+        roofline = {"bound": "tensor", "kernel": kname,
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": 8.0 * m * (0.5 * N * N + 2.0 * N * min(C, 4096)),
                     "peak_source": "cuBLAS DGEMM fp64 8192^3 measured live in this run (MEASURED_PEAKS.json holds HBM and bf16 "
                                    "only; FP64 DMMA issue peak measured at 37.2 TFLOP/s, profiles/fp64_pipe_probe_r01.json)",
                     "flops_per_launch": cnt["trmm_flops"] / max(cnt["trmm_launches"], 1),
