@@ -82,6 +82,7 @@ constexpr int kMaxFitCtx = 4;
 struct aoed_gp {
     int device = 0, d = 0, m = 0, nu = 1, DP = 8;
     int N = 0, Npad = 0, Kpad = 0, mTiles = 0, JS = 1, jchunk = 0;  // JS: CAPACITY of the training-index split (partials)
+    int cap_Npad = 0;  // row capacity the device buffers were allocated for (re-used while N stays in the same 128-bucket)
     int occ_xcov = 2, occ_gradsum = 5;  // resident CTAs per SM of the two thread-per-candidate kernels
     bool has_train = false, has_theta = false;
     std::vector<double> theta, y_mean, y_scale, lml, Xn, Yn;
@@ -103,7 +104,8 @@ struct aoed_gp {
     int trmm_variant = 0;           // 0: persistent TMA kernel, 64 / 128: cp.async tiled kernel with that column tile
     int ssf = PT_SS_PER_TILE;       // sum-of-squares partials per 128-row tile (4 for the TMA kernel, 1 otherwise)
     FitCtx fit[kMaxFitCtx];
-    int nfit = 0;
+    int nfit = 0;        // contexts with a stream + handle
+    int nfit_sized = 0;  // ... of which have buffers for the current capacity
     double *dThetaB = nullptr, *dResB = nullptr;  // batched LML inputs / results
     int* dObjB = nullptr;
     int batchCap = 0;
@@ -153,12 +155,10 @@ void free_model(aoed_gp* gp) {
         }
         if (c.info) cudaFree(c.info);
         c.info = nullptr;
-        if (c.solver) cusolverDnDestroy(c.solver);
-        c.solver = nullptr;
-        if (c.stream) cudaStreamDestroy(c.stream);
-        c.stream = nullptr;
+        c.lwork = 0;
     }
-    gp->nfit = 0;
+    gp->nfit_sized = 0;  // streams and cuSOLVER handles survive (creating a handle costs tens of milliseconds)
+    gp->cap_Npad = 0;
     if (gp->dThetaB) cudaFree(gp->dThetaB);
     if (gp->dResB) cudaFree(gp->dResB);
     if (gp->dObjB) cudaFree(gp->dObjB);
@@ -179,6 +179,7 @@ int64_t chunk_cap() {
 }
 
 int make_map_2d(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+int size_fit_ctx_work(aoed_gp* gp, FitCtx& c);
 
 int ensure_ws(aoed_gp* gp, Workspace& w, int64_t cols, bool staging) {
     cols = round_up64(cols, 128);
@@ -715,6 +716,11 @@ int aoed_gp_destroy(aoed_gp_t* gp) {
     DeviceGuard guard_(gp->device);
     cudaDeviceSynchronize();
     free_model(gp);
+    for (int i = 0; i < gp->nfit; ++i) {
+        if (gp->fit[i].solver) cusolverDnDestroy(gp->fit[i].solver);
+        if (gp->fit[i].stream) cudaStreamDestroy(gp->fit[i].stream);
+    }
+    gp->nfit = 0;
     if (gp->solver) cusolverDnDestroy(gp->solver);
     if (gp->blas) cublasDestroy(gp->blas);
     if (gp->ev0) cudaEventDestroy(gp->ev0);
@@ -732,15 +738,18 @@ int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const doub
     DeviceGuard guard_(gp->device);
     CU(guard_.err);
     CU(cudaDeviceSynchronize());
-    free_model(gp);
     const int N = n_train, d = gp->d, m = gp->m;
+    const int prevN = gp->N;
+    // MOBO refits every iteration with a few more rows: keep every allocation (model, fit scratch, workspaces, cuSOLVER
+    // handles, TMA descriptors) while N stays in the same 128-row bucket
+    const bool reuse = gp->cap_Npad == round_up(N, TM);
+    if (!reuse) free_model(gp);
     gp->N = N;
     gp->Npad = round_up(N, TM);
     gp->Kpad = round_up(N, TK);
     gp->mTiles = gp->Npad / TM;
-    gp->JS = std::min(16, std::max(1, (N + XC_JT - 1) / XC_JT));  // capacity; the split per launch is choose_split()
+    gp->JS = 16;  // capacity of the training-index split (partial-sum buffers); the split per launch is choose_split()
     gp->jchunk = round_up((N + gp->JS - 1) / gp->JS, XC_JT);
-    gp->JS = (N + gp->jchunk - 1) / gp->jchunk;
     gp->has_train = true;
     gp->has_theta = false;
     gp->Xn.assign(h_Xn, h_Xn + size_t(N) * d);
@@ -751,37 +760,59 @@ int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const doub
     if (h_y_scale) gp->y_scale.assign(h_y_scale, h_y_scale + m);
     gp->lml.assign(m, std::numeric_limits<double>::quiet_NaN());
     const size_t Np = gp->Npad;
-    CU(cudaMalloc(&gp->dX, size_t(N) * d * sizeof(double)));
+    if (!reuse) {
+        CU(cudaMalloc(&gp->dX, Np * d * sizeof(double)));
+        CU(cudaMalloc(&gp->dY, size_t(m) * Np * sizeof(double)));
+        CU(cudaMalloc(&gp->dTs, size_t(m) * Np * gp->DP * sizeof(double)));
+        CU(cudaMalloc(&gp->dAlpha, size_t(m) * Np * sizeof(double)));
+        CU(cudaMalloc(&gp->dEll, size_t(m) * gp->DP * sizeof(double)));
+        CU(cudaMalloc(&gp->dModel, size_t(m) * sizeof(ModelDev)));
+        CU(cudaMalloc(&gp->dLinv, size_t(m) * Np * Np * sizeof(double)));
+        CU(cudaMalloc(&gp->dLinvT, size_t(m) * Np * Np * sizeof(double)));
+        CU(cudaMalloc(&gp->dL, size_t(m) * Np * Np * sizeof(double)));
+        CU(cudaMalloc(&gp->dTickets, 64 * sizeof(int)));
+        if (gp->trmm_variant == 0) {
+            CHK(make_map_2d(&gp->mapLinv, gp->dLinv, int64_t(m) * Np, Np, Np, TM));
+            CHK(make_map_2d(&gp->mapLinvT, gp->dLinvT, int64_t(m) * Np, Np, Np, TM));
+        }
+        CU(cudaMalloc(&gp->dK, Np * Np * sizeof(double)));
+        CU(cudaMalloc(&gp->dC1C2, size_t(m) * 2 * sizeof(double)));
+        CU(cudaMalloc(&gp->dInfo, sizeof(int)));
+        const size_t nbp = (Np + 15) / 16;
+        CU(cudaMalloc(&gp->dGradPartial, nbp * nbp * (gp->DP + 2) * sizeof(double)));
+        CU(cudaMalloc(&gp->dGrad, size_t(gp->DP + 2) * sizeof(double)));
+        gp->solverLwork = 0;
+        gp->cap_Npad = gp->Npad;
+    } else if (prevN != N) {
+        // slab rows in [N, Kpad) feed the triangular products as k-rows against zero columns of the factor: keep them
+        // free of stale values from the previous training set
+        for (auto& w : gp->ws) {
+            if (w.cols == 0) continue;
+            const size_t slab = size_t(m) * Np * size_t(w.cols) * sizeof(double);
+            CU(cudaMemsetAsync(w.KsT, 0, slab, nullptr));
+            CU(cudaMemsetAsync(w.Gr, 0, slab, nullptr));
+            CU(cudaMemsetAsync(w.W, 0, slab, nullptr));
+            CU(cudaMemsetAsync(w.V, 0, slab, nullptr));
+        }
+        CU(cudaDeviceSynchronize());
+    }
     CU(cudaMemcpy(gp->dX, h_Xn, size_t(N) * d * sizeof(double), cudaMemcpyHostToDevice));
     std::vector<double> yt(size_t(m) * Np, 0.0);
     for (int o = 0; o < m; ++o)
         for (int i = 0; i < N; ++i) yt[size_t(o) * Np + i] = h_Yn[size_t(i) * m + o];
-    CU(cudaMalloc(&gp->dY, yt.size() * sizeof(double)));
     CU(cudaMemcpy(gp->dY, yt.data(), yt.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&gp->dTs, size_t(m) * Np * gp->DP * sizeof(double)));
-    CU(cudaMalloc(&gp->dAlpha, size_t(m) * Np * sizeof(double)));
-    CU(cudaMalloc(&gp->dEll, size_t(m) * gp->DP * sizeof(double)));
-    CU(cudaMalloc(&gp->dModel, size_t(m) * sizeof(ModelDev)));
-    CU(cudaMalloc(&gp->dLinv, size_t(m) * Np * Np * sizeof(double)));
-    CU(cudaMalloc(&gp->dLinvT, size_t(m) * Np * Np * sizeof(double)));
-    CU(cudaMalloc(&gp->dL, size_t(m) * Np * Np * sizeof(double)));
-    CU(cudaMalloc(&gp->dTickets, 64 * sizeof(int)));
-    if (gp->trmm_variant == 0) {
-        CHK(make_map_2d(&gp->mapLinv, gp->dLinv, int64_t(m) * Np, Np, Np, TM));
-        CHK(make_map_2d(&gp->mapLinvT, gp->dLinvT, int64_t(m) * Np, Np, Np, TM));
-    }
-    CU(cudaMalloc(&gp->dK, Np * Np * sizeof(double)));
-    CU(cudaMalloc(&gp->dC1C2, size_t(m) * 2 * sizeof(double)));
-    CU(cudaMalloc(&gp->dInfo, sizeof(int)));
-    const int nb = (N + 15) / 16;
-    CU(cudaMalloc(&gp->dGradPartial, size_t(nb) * nb * (gp->DP + 2) * sizeof(double)));
-    CU(cudaMalloc(&gp->dGrad, size_t(gp->DP + 2) * sizeof(double)));
     int lwork = 0;
     if (cusolverDnDpotrf_bufferSize(gp->solver, CUBLAS_FILL_MODE_UPPER, N, gp->dK, gp->Npad, &lwork) !=
         CUSOLVER_STATUS_SUCCESS)
         return fail(AOED_ERR_CUDA, "potrf_bufferSize failed");
-    gp->solverLwork = lwork;
-    CU(cudaMalloc(&gp->dSolverWork, size_t(std::max(lwork, 1)) * sizeof(double)));
+    if (lwork > gp->solverLwork || gp->dSolverWork == nullptr) {
+        if (gp->dSolverWork) cudaFree(gp->dSolverWork);
+        gp->dSolverWork = nullptr;
+        CU(cudaMalloc(&gp->dSolverWork, size_t(std::max(lwork, 1)) * sizeof(double)));
+        gp->solverLwork = std::max(lwork, 1);
+    }
+    // per-stream cuSOLVER scratch of the blocked LML path follows N as well
+    for (int i = 0; i < gp->nfit_sized; ++i) CHK(size_fit_ctx_work(gp, gp->fit[i]));
     return AOED_OK;
 }
 
@@ -843,31 +874,44 @@ int ensure_batch(aoed_gp* gp, int n_prob) {
     return AOED_OK;
 }
 
+int size_fit_ctx_work(aoed_gp* gp, FitCtx& c) {
+    int l1 = 0, l2 = 0;
+    if (cusolverDnDpotrf_bufferSize(c.solver, CUBLAS_FILL_MODE_UPPER, gp->N, c.K, gp->Npad, &l1) != CUSOLVER_STATUS_SUCCESS ||
+        cusolverDnDpotri_bufferSize(c.solver, CUBLAS_FILL_MODE_UPPER, gp->N, c.K, gp->Npad, &l2) != CUSOLVER_STATUS_SUCCESS)
+        return fail(AOED_ERR_CUDA, "cusolver bufferSize failed");
+    const int need = std::max(std::max(l1, l2), 1);
+    if (need > c.lwork || c.work == nullptr) {
+        if (c.work) cudaFree(c.work);
+        c.work = nullptr;
+        CU(cudaMalloc(&c.work, size_t(need) * sizeof(double)));
+        c.lwork = need;
+    }
+    return AOED_OK;
+}
+
 int ensure_fit_ctx(aoed_gp* gp) {
-    if (gp->nfit > 0) return AOED_OK;
-    const int N = gp->N, Npad = gp->Npad, DP = gp->DP;
-    const int n = (N <= 1024) ? kMaxFitCtx : 2;  // small problems do not fill the GPU alone: overlap them
+    const int Npad = gp->Npad, DP = gp->DP;
+    const int n = (gp->N <= 1024) ? kMaxFitCtx : 2;  // small problems do not fill the GPU alone: overlap them
     const size_t NN = size_t(Npad) * Npad;
-    const int nb = (N + 15) / 16;
-    for (int i = 0; i < n; ++i) {
+    const size_t nbp = (size_t(Npad) + 15) / 16;
+    for (int i = gp->nfit; i < n; ++i) {  // streams + handles: created once per model handle
         FitCtx& c = gp->fit[i];
         CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         if (cusolverDnCreate(&c.solver) != CUSOLVER_STATUS_SUCCESS) return fail(AOED_ERR_CUDA, "cusolverDnCreate failed");
         cusolverDnSetStream(c.solver, c.stream);
+        gp->nfit = i + 1;
+    }
+    for (int i = gp->nfit_sized; i < gp->nfit; ++i) {  // buffers: per row capacity
+        FitCtx& c = gp->fit[i];
         CU(cudaMalloc(&c.K, NN * sizeof(double)));
         CU(cudaMemsetAsync(c.K, 0, NN * sizeof(double), c.stream));
         CU(cudaMalloc(&c.Ts, size_t(Npad) * DP * sizeof(double)));
         CU(cudaMalloc(&c.c1c2, 2 * sizeof(double)));
         CU(cudaMalloc(&c.alpha, size_t(Npad) * sizeof(double)));
-        CU(cudaMalloc(&c.partial, size_t(nb) * nb * (DP + 2) * sizeof(double)));
+        CU(cudaMalloc(&c.partial, nbp * nbp * (DP + 2) * sizeof(double)));
         CU(cudaMalloc(&c.info, 2 * sizeof(int)));
-        int l1 = 0, l2 = 0;
-        if (cusolverDnDpotrf_bufferSize(c.solver, CUBLAS_FILL_MODE_UPPER, N, c.K, Npad, &l1) != CUSOLVER_STATUS_SUCCESS ||
-            cusolverDnDpotri_bufferSize(c.solver, CUBLAS_FILL_MODE_UPPER, N, c.K, Npad, &l2) != CUSOLVER_STATUS_SUCCESS)
-            return fail(AOED_ERR_CUDA, "cusolver bufferSize failed");
-        c.lwork = std::max(std::max(l1, l2), 1);
-        CU(cudaMalloc(&c.work, size_t(c.lwork) * sizeof(double)));
-        gp->nfit = i + 1;
+        CHK(size_fit_ctx_work(gp, c));
+        gp->nfit_sized = i + 1;
     }
     return AOED_OK;
 }
@@ -1013,10 +1057,11 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
         gp->n_fit_small += n_prob;
     } else {
         CHK(ensure_fit_ctx(gp));
+        const int nctx = std::min(gp->nfit_sized, (N <= 1024) ? kMaxFitCtx : 2);
         CU(cudaStreamSynchronize(s0));  // thetas uploaded
         const int nb = (N + 15) / 16;
         for (int b = 0; b < n_prob; ++b) {
-            FitCtx& c = gp->fit[b % gp->nfit];
+            FitCtx& c = gp->fit[b % nctx];
             cudaStream_t s = c.stream;
             const int o = h_obj[b];
             double* res = gp->dResB + size_t(b) * (p + 1);
@@ -1050,7 +1095,7 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
             }
             CU(cudaGetLastError());
         }
-        for (int i = 0; i < gp->nfit; ++i) CU(cudaStreamSynchronize(gp->fit[i].stream));
+        for (int i = 0; i < nctx; ++i) CU(cudaStreamSynchronize(gp->fit[i].stream));
         gp->n_fit_blocked += n_prob;
     }
     std::vector<double> res(size_t(n_prob) * (p + 1));

@@ -82,8 +82,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def blas_threads():
+    """Lets the CPU baseline use every host core even under torchrun (which exports OMP_NUM_THREADS=1): returns the
+    (context manager, thread count) to run the oracle under."""
+    from threadpoolctl import threadpool_info, threadpool_limits
+    n = os.cpu_count() or 1
+    ctx = threadpool_limits(limits=n)
+    used = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    return ctx, used
+
+
 def cpu_port_rate(n_train, d, m, nu, budget_s, chunk=1024):
     """The CPU oracle (vectorised numpy restatement of gp.py:141-253 + ucb.py) on a bounded sample of the workload."""
+    ctx, _ = blas_threads()
+    with ctx:
+        return _cpu_port_rate(n_train, d, m, nu, budget_s, chunk)
+
+
+def _cpu_port_rate(n_train, d, m, nu, budget_s, chunk=1024):
     from oracle import gp_oracle as go
     X, Y, thetas = make_problem(n_train, d, m)
     orc = go.GPOracle(d, m, nu=nu).fit(X, Y, thetas=thetas)
@@ -108,7 +124,7 @@ def run_reference(args):
     if rank != 0:
         return
     w = WORKLOAD
-    cores = os.cpu_count()
+    cores = blas_threads()[1]
     rates = []
     for _ in range(args.warmup):
         cpu_port_rate(w["n_train"], w["n_var"], w["n_obj"], w["nu"], 1.0)
@@ -145,6 +161,10 @@ def dgemm_peak(torch, dev):
 
 
 def run_ours(args):
+    # exactly ONE line goes to stdout: library chatter (e.g. NCCL's version banner) is diverted to stderr until the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from autooed_b200 import GaussianProcess, UpperConfidenceBound, _lib
@@ -263,10 +283,13 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": C * d * 8,
                         "d2h_bytes_per_step": C * m * (1 + d) * 8},
                 "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": blas_threads()[1], "kind": "port",
                                  "sample": f"{cpu_done} candidates of the same workload in {cpu_el:.1f}s (oracle/gp_oracle.py, numpy BLAS threads unrestricted)"},
                 "clocks": clocks, "device_host_legs_identical": same}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

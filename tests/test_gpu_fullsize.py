@@ -1,0 +1,100 @@
+"""Parity at BASELINE.json's full problem sizes (c4: N=2000 d=20 m=3; c5: N=4000 d=32 m=3).  The oracle checks a sample of
+rows directly (it needs seconds for a few hundred candidates at these N); the whole batch is covered by size-independent
+properties: determinism, invariance to how the batch is chunked, the UCB identity A = F - lambda S / dA = dF - lambda dS
+computed from separately requested outputs, 0 <= S <= prior std, and S ~ 0 at training points."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as go
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+def make_problem(n_train, d, m, seed=0):
+    """bench.py's synthetic generator."""
+    rng = np.random.default_rng(seed)
+    X = rng.random((n_train, d))
+    W = rng.standard_normal((d, m))
+    Y = np.sin(X @ W) + 0.1 * (X ** 2) @ np.abs(W)
+    rng1 = np.random.default_rng(seed + 1)
+    thetas = np.stack([np.concatenate([[0.0], rng1.uniform(-0.5, 1.0, d), [math.log(0.01)]]) for _ in range(m)])
+    return X, Y, thetas
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("cfg", [("c4", 2000, 20, 3, 5, 9000, 192), ("c5", 4000, 32, 3, 5, 4500, 64),
+                                 ("c4-matern12", 2000, 20, 3, 1, 4200, 64)])
+def test_full_size_posterior_and_ucb(cfg):
+    from autooed_b200 import GaussianProcess, UpperConfidenceBound
+    from autooed_b200.problem import SimpleProblem
+    name, N, d, m, nu, C, n_check = cfg
+    X, Y, thetas = make_problem(N, d, m)
+    gp = GaussianProcess(SimpleProblem(d, m), nu=nu)
+    gp.fit_fixed(X, Y, thetas)
+    acq = UpperConfidenceBound(gp)
+    acq.fit(X, Y)
+    rng = np.random.default_rng(2)
+    Xs = rng.random((C, d))
+    Xs[:5] = X[:5]  # candidates sitting on training points
+    out = gp.evaluate(Xs, std=True, gradient=True)
+    A, dA, _ = acq.evaluate(Xs, gradient=True)
+
+    # --- sample of rows against the CPU oracle (same triangular algorithm) ---
+    orc = go.GPOracle(d, m, nu=nu).fit(X, Y, thetas=thetas)
+    idx = np.concatenate([np.arange(8), rng.choice(C, n_check - 8, replace=False)])
+    ref = orc.evaluate(Xs[idx], std=True, gradient=True, var_form="chol", chunk=64)
+    cond = max(np.linalg.cond(st.L) ** 2 for st in orc.states)
+    tol = max(1e-8, 100 * cond * EPS)
+    assert rel(out["F"][idx], ref["F"]) < tol
+    assert rel(out["dF"][idx], ref["dF"]) < tol
+    prior = np.exp(thetas[:, 0]) + np.exp(thetas[:, -1])
+    ys = orc.norm.y_scale
+    dv = np.abs((out["S"][idx] / ys) ** 2 - (ref["S"] / ys) ** 2) / prior
+    assert dv.max() < max(1e-10, tol * 1e-2)
+    ok = ((ref["S"] / ys) ** 2 / prior > 1e-6).all(axis=1)
+    assert ok.sum() > n_check // 2
+    assert rel(out["dS"][idx][ok], ref["dS"][ok]) < max(1e-7, tol * 10)
+    oA, odA, _ = go.acquisition("ucb", ref, True, False, n_sample=N)
+    assert rel(A[idx], oA) < tol
+    assert rel(dA[idx][ok], odA[ok]) < max(1e-7, tol * 10)
+
+    # --- properties over the WHOLE batch ---
+    lam = math.sqrt(math.log(N) / N)
+    assert np.allclose(A, out["F"] - lam * out["S"], rtol=1e-13, atol=1e-13)  # ucb.py:28
+    assert np.allclose(dA, out["dF"] - lam * out["dS"], rtol=1e-12, atol=1e-12)  # ucb.py:40
+    assert (out["S"] >= 0).all() and (out["S"] <= np.sqrt(prior) * ys * (1 + 1e-12)).all()
+    assert (out["S"][:5] / (np.sqrt(prior) * ys) < 1e-3).all()  # on training points sigma^2 ~ jitter
+    assert np.isfinite(out["dS"]).all() and np.isfinite(dA).all()
+    again = gp.evaluate(Xs, std=True, gradient=True)
+    for k in ("F", "S", "dF", "dS"):
+        assert np.array_equal(out[k], again[k]), k  # deterministic
+    # chunking invariance: a differently sized call sees other tile / split choices, same numbers up to summation order
+    part = gp.evaluate(Xs[1000:1300], std=True, gradient=True)
+    assert np.allclose(part["F"], out["F"][1000:1300], rtol=1e-11, atol=1e-12)
+    assert np.allclose(part["S"], out["S"][1000:1300], rtol=1e-8, atol=1e-11)
+    assert np.allclose(part["dF"], out["dF"][1000:1300], rtol=1e-9, atol=1e-11)
+    okp = (part["S"] / ys) ** 2 / prior > 1e-6
+    assert np.allclose(part["dS"][okp.all(axis=1)], out["dS"][1000:1300][okp.all(axis=1)], rtol=1e-6, atol=1e-9)
+
+
+def test_full_size_lml_gradient():
+    """One c4-sized log-marginal-likelihood + gradient (blocked path, N=2000) against the oracle (3 s on the CPU)."""
+    from autooed_b200 import GaussianProcess
+    from autooed_b200.problem import SimpleProblem
+    N, d, m = 2000, 20, 3
+    X, Y, thetas = make_problem(N, d, m)
+    Yn = (Y - Y.mean(0)) / Y.std(0)
+    gp = GaussianProcess(SimpleProblem(d, m), nu=5)
+    gp._set_train(X, Yn)
+    lml, grad = gp.log_marginal_likelihood_batch([0, 1, 2, 1], np.vstack([thetas, go.initial_theta(d)[None]]), True)
+    rv, rg = go.lml_and_grad(thetas[1], X, Yn[:, 1], 5)
+    assert abs(lml[1] - rv) <= 1e-8 * abs(rv)
+    assert np.abs(grad[1] - rg).max() <= 1e-6 * np.abs(rg).max()
+    assert np.isfinite(lml).all() and np.isfinite(grad).all()
+    assert gp.fit_counters()["blocked"] == 4
