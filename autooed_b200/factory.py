@@ -3,11 +3,13 @@ a maintainer can route 'gp' / 'ei' / 'identity' / 'pi' / 'ucb' / 'hvi' to the B2
 from autooed_b200.surrogate_model import GaussianProcess
 from autooed_b200.acquisition import Identity, UpperConfidenceBound, ExpectedImprovement, ProbabilityOfImprovement
 from autooed_b200.selection import HypervolumeImprovement
+from autooed_b200.solver import NSGA2
 
 _SURROGATES = {'gp': GaussianProcess}
 _ACQUISITIONS = {'ei': ExpectedImprovement, 'identity': Identity, 'pi': ProbabilityOfImprovement,
                  'ucb': UpperConfidenceBound}
 _SELECTIONS = {'hvi': HypervolumeImprovement}
+_SOLVERS = {'nsga2': NSGA2}
 
 
 def get_surrogate_model(name):
@@ -28,6 +30,12 @@ def get_selection(name):
     raise Exception(f'Undefined selection {name}')
 
 
+def get_solver(name):
+    if name in _SOLVERS:
+        return _SOLVERS[name]
+    raise Exception(f'Undefined solver {name}')
+
+
 def _name(name, params, key):
     # the CLI spells module_cfg[...]['surrogate'], GUI configs use ['name'] (SURVEY.md §5 "Config / flag system")
     if name is not None:
@@ -45,3 +53,7 @@ def init_acquisition(name, params, surrogate_model):
 
 def init_selection(name, params, surrogate_model):
     return get_selection(_name(name, params, 'selection'))(surrogate_model, **params)
+
+
+def init_solver(name, params, problem):
+    return get_solver(_name(name, params, 'solver'))(problem, **params)

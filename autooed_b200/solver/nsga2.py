@@ -1,0 +1,164 @@
+"""NSGA-II on the surrogate problem — the immediate caller of the GPU acquisition.
+
+Reference: `autooed/mobo/solver/nsga2.py:13-30` delegates to pymoo 0.4.1 `NSGA2(pop_size)` + `minimize(..., ('n_gen', G))`.
+pymoo is not part of this repository, so the algorithm is written out here with pymoo 0.4.1's defaults (SURVEY.md
+Appendix F): the initial population is the given sampling as is; binary tournament on (rank, crowding distance);
+simulated binary crossover (prob 0.9, eta 15, per-variable exchange prob 0.5); polynomial mutation (eta 20, prob
+1/n_var); duplicate elimination; n_offsprings = pop_size; rank-and-crowding survival; generation 1 is the evaluation of
+the initial population.  Populations are NOT seed-for-seed identical with pymoo (different RNG call order); every
+acquisition evaluation inside the loop is the parity-tested device call.
+
+Every generation costs one batched `problem.evaluate` (pop_size rows) — the work the B200 path accelerates — plus
+O(pop^2) host bookkeeping; non-dominated sorting runs on the GPU when `rank_fn` is the default."""
+import numpy as np
+
+from autooed_b200.solver.base import Solver
+
+
+def lhs(n_var, n_samples):
+    """Random Latin-hypercube design in [0, 1]^n_var (one point per stratum and dimension)."""
+    u = (np.random.rand(n_samples, n_var) + np.arange(n_samples)[:, None]) / n_samples
+    for k in range(n_var):
+        u[:, k] = u[np.random.permutation(n_samples), k]
+    return u
+
+
+def crowding_distance(F):
+    """Crowding distance of one front (larger = lonelier; boundary points get +inf)."""
+    n, m = F.shape
+    if n <= 2:
+        return np.full(n, np.inf)
+    dist = np.zeros(n)
+    for k in range(m):
+        order = np.argsort(F[:, k], kind='stable')
+        f = F[order, k]
+        span = f[-1] - f[0]
+        d = np.zeros(n)
+        d[0] = d[-1] = np.inf
+        if span > 0:
+            d[1:-1] = (f[2:] - f[:-2]) / span
+        dist[order] += d
+    return dist
+
+
+def _default_rank(F):
+    from autooed_b200.utils.pareto import pareto_rank
+    return pareto_rank(F)
+
+
+class NSGA2Algorithm:
+    def __init__(self, pop_size=200, crossover_prob=0.9, eta_c=15.0, eta_m=20.0, rank_fn=None):
+        self.pop_size = pop_size
+        self.crossover_prob, self.eta_c, self.eta_m = crossover_prob, eta_c, eta_m
+        self.rank_fn = rank_fn or _default_rank
+        self.n_eval = 0
+
+    # -- variation -------------------------------------------------------------------------------------------------
+    def _tournament(self, rank, crowd, n):
+        a, b = np.random.randint(len(rank), size=n), np.random.randint(len(rank), size=n)
+        better = (rank[a] < rank[b]) | ((rank[a] == rank[b]) & (crowd[a] > crowd[b]))
+        tie = (rank[a] == rank[b]) & (crowd[a] == crowd[b])
+        pick_a = np.where(tie, np.random.rand(n) < 0.5, better)
+        return np.where(pick_a, a, b)
+
+    def _sbx(self, P1, P2, xl, xu):
+        n, d = P1.shape
+        C1, C2 = P1.copy(), P2.copy()
+        do_pair = np.random.rand(n) < self.crossover_prob
+        do_var = (np.random.rand(n, d) < 0.5) & do_pair[:, None] & (np.abs(P1 - P2) > 1e-14)
+        y1, y2 = np.minimum(P1, P2), np.maximum(P1, P2)
+        delta = np.where(do_var, y2 - y1, 1.0)
+        u = np.random.rand(n, d)
+
+        def child(beta_bound):
+            alpha = 2.0 - np.power(beta_bound, -(self.eta_c + 1.0))
+            return np.where(u <= 1.0 / alpha, np.power(u * alpha, 1.0 / (self.eta_c + 1.0)),
+                            np.power(1.0 / (2.0 - u * alpha), 1.0 / (self.eta_c + 1.0)))
+
+        betaq1 = child(1.0 + 2.0 * (y1 - xl) / delta)
+        betaq2 = child(1.0 + 2.0 * (xu - y2) / delta)
+        c1 = np.clip(0.5 * ((y1 + y2) - betaq1 * delta), xl, xu)
+        c2 = np.clip(0.5 * ((y1 + y2) + betaq2 * delta), xl, xu)
+        swap = np.random.rand(n, d) < 0.5
+        C1 = np.where(do_var, np.where(swap, c2, c1), C1)
+        C2 = np.where(do_var, np.where(swap, c1, c2), C2)
+        return C1, C2
+
+    def _mutate(self, X, xl, xu):
+        n, d = X.shape
+        do = np.random.rand(n, d) < 1.0 / d
+        span = np.where(xu > xl, xu - xl, 1.0)
+        d1, d2 = (X - xl) / span, (xu - X) / span
+        u = np.random.rand(n, d)
+        p = 1.0 / (self.eta_m + 1.0)
+        lo = np.power(2.0 * u + (1.0 - 2.0 * u) * np.power(1.0 - d1, self.eta_m + 1.0), p) - 1.0
+        hi = 1.0 - np.power(2.0 * (1.0 - u) + 2.0 * (u - 0.5) * np.power(1.0 - d2, self.eta_m + 1.0), p)
+        dq = np.where(u <= 0.5, lo, hi)
+        return np.clip(np.where(do, X + dq * span, X), xl, xu)
+
+    @staticmethod
+    def _drop_duplicates(X, others, eps=1e-16):
+        """Offspring equal (squared distance <= eps) to a population member or an earlier offspring are discarded."""
+        keep = np.ones(len(X), dtype=bool)
+        if len(others):
+            d2 = ((X[:, None, :] - others[None, :, :]) ** 2).sum(-1)
+            keep &= ~(d2 <= eps).any(axis=1)
+        d2 = ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1)
+        keep &= ~np.triu(d2 <= eps, 1).any(axis=0)
+        return X[keep]
+
+    # -- survival --------------------------------------------------------------------------------------------------
+    def _rank_and_crowding(self, F):
+        rank = np.asarray(self.rank_fn(F))
+        crowd = np.zeros(len(F))
+        for r in np.unique(rank):
+            idx = np.flatnonzero(rank == r)
+            crowd[idx] = crowding_distance(F[idx])
+        return rank, crowd
+
+    def _survive(self, X, F):
+        rank, crowd = self._rank_and_crowding(F)
+        if len(X) > self.pop_size:
+            order = np.lexsort((-crowd, rank))[:self.pop_size]  # fronts in order, last front by crowding descending
+            X, F, rank, crowd = X[order], F[order], rank[order], crowd[order]
+        return X, F, rank, crowd
+
+    # -- driver ----------------------------------------------------------------------------------------------------
+    def minimize(self, problem, X0, n_gen):
+        xl, xu = np.asarray(problem.xl, dtype=float), np.asarray(problem.xu, dtype=float)
+        X = np.array(X0, dtype=float)
+        F = np.asarray(problem.evaluate(X, return_values_of=['F']))
+        self.n_eval = len(X)
+        X, F, rank, crowd = self._survive(X, F)
+        for _ in range(n_gen - 1):
+            off = np.empty((0, X.shape[1]))
+            for _attempt in range(10):  # refill after duplicate elimination, as pymoo's mating loop does
+                need = self.pop_size - len(off)
+                if need <= 0:
+                    break
+                n_pairs = (need + 1) // 2
+                pa = self._tournament(rank, crowd, n_pairs)
+                pb = self._tournament(rank, crowd, n_pairs)
+                c1, c2 = self._sbx(X[pa], X[pb], xl, xu)
+                cand = self._mutate(np.vstack([c1, c2])[:need], xl, xu)
+                off = np.vstack([off, self._drop_duplicates(cand, np.vstack([X, off]))])
+            if len(off) == 0:
+                break
+            Foff = np.asarray(problem.evaluate(off, return_values_of=['F']))
+            self.n_eval += len(off)
+            X, F, rank, crowd = self._survive(np.vstack([X, off]), np.vstack([F, Foff]))
+        return X, F
+
+
+class NSGA2(Solver):
+    '''
+    Solver based on NSGA-II.
+    '''
+    def __init__(self, problem, n_gen=200, pop_size=200, rank_fn=None, **kwargs):
+        super().__init__(problem)
+        self.n_gen = n_gen
+        self.algo = NSGA2Algorithm(pop_size=pop_size, rank_fn=rank_fn)
+
+    def _solve(self, X, Y, batch_size):
+        X = np.vstack([X, lhs(X.shape[1], batch_size)])  # nsga2.py:25 (the reference samples the unit cube as well)
+        return self.algo.minimize(self.problem, X, self.n_gen)

@@ -294,6 +294,183 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# =====================================================================================================================
+# secondary measurements (not the contract line): `--mode fit` and `--mode mobo` print one JSON line per measurement
+# =====================================================================================================================
+def _fit_data(N, d, m, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.random((N, d))
+    Y = np.sin(X @ rng.standard_normal((d, m))) + 0.1 * (X ** 2) @ np.abs(rng.standard_normal((d, m))) \
+        + 0.02 * rng.standard_normal((N, m))
+    return X, Y
+
+
+def run_fit_mode(args):
+    """Hyper-parameter fit path: batched LML + gradient per device batch and full L-BFGS-B fits,
+    next to the CPU oracle (sklearn's formulation restated in numpy) with all host threads."""
+    from autooed_b200 import GaussianProcess
+    from autooed_b200.problem import SimpleProblem
+    from oracle import gp_oracle as go
+    ctx, threads = blas_threads()
+
+    def lml_batches(N, d, m, nu, batches, reps=5, cpu_calls=2):
+        X, Y = _fit_data(N, d, m)
+        Yn = (Y - Y.mean(0)) / Y.std(0)
+        gp = GaussianProcess(SimpleProblem(d, m), nu=nu)
+        gp._set_train(X, Yn)
+        lo, hi = go.theta_bounds(d).T
+        rng = np.random.default_rng(1)
+        with ctx:
+            t0 = time.perf_counter()
+            for i in range(cpu_calls):
+                go.lml_and_grad(rng.uniform(lo, hi) * 0.3, X, Yn[:, i % m], nu)
+            cpu_s = (time.perf_counter() - t0) / cpu_calls
+        for B in batches:
+            obj = np.arange(B) % m
+            th = rng.uniform(lo, hi, (B, d + 2)) * 0.3
+            gp.log_marginal_likelihood_batch(obj, th, True)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                gp.log_marginal_likelihood_batch(obj, th, True)
+            dt = (time.perf_counter() - t0) / reps
+            print(json.dumps({"mode": "fit", "what": "lml+grad batch", "N": N, "d": d, "nu": nu, "problems": B,
+                              "ms_per_batch": 1e3 * dt, "problems_per_s": B / dt, "cpu_port_ms_per_problem": 1e3 * cpu_s,
+                              "cpu_threads": threads, "speedup_vs_cpu_serial": cpu_s * B / dt,
+                              "path": "shared-memory kernel" if N <= 232 else "blocked multi-stream"}), flush=True)
+
+    def full_fit(N, d, m, nu, n_restarts):
+        X, Y = _fit_data(N, d, m)
+        gp = GaussianProcess(SimpleProblem(d, m), nu=nu, n_restarts=n_restarts, seed=0)
+        gp.fit(X, Y)
+        t0 = time.perf_counter()
+        gp.fit(X, Y)
+        gpu_s = time.perf_counter() - t0
+        with ctx:
+            t0 = time.perf_counter()
+            orc = go.GPOracle(d, m, nu=nu).fit(X, Y)
+            cpu_s = time.perf_counter() - t0
+        print(json.dumps({"mode": "fit", "what": "full fit", "N": N, "d": d, "m": m, "nu": nu,
+                          "gpu_starts_per_objective": 1 + n_restarts, "gpu_s": gpu_s,
+                          "gpu_fit_info": {k: v for k, v in gp.fit_info.items() if k != "nfev"},
+                          "cpu_port_s_single_start": cpu_s, "cpu_threads": threads, "cpu_nfev": orc.nfev}), flush=True)
+
+    lml_batches(200, 6, 2, 5, [1, 2, 16, 148, 592])
+    lml_batches(500, 10, 3, 5, [3, 48])
+    lml_batches(2000, 20, 3, 5, [3, 48], reps=2, cpu_calls=1)
+    full_fit(200, 6, 2, 5, 0)
+    full_fit(200, 6, 2, 5, 15)
+    full_fit(500, 10, 3, 5, 0)
+
+
+class _OracleSurrogate:
+    """CPU stand-in with the plugin surface the solver / selection need (test infrastructure: oracle/gp_oracle.py)."""
+
+    def __init__(self, problem, nu):
+        from autooed_b200.problem import ContinuousTransformation
+        from autooed_b200.utils.normalization import StandardNormalization
+        self.problem, self.nu = problem, nu
+        self.n_var, self.n_obj = problem.n_var, problem.n_obj
+        self.transformation = ContinuousTransformation()
+        self.normalization = StandardNormalization(np.array([problem.xl, problem.xu]))
+        self.fitted = False
+
+    def fit(self, X, Y):
+        from oracle import gp_oracle as go
+        self.orc = go.GPOracle(self.n_var, self.n_obj, self.problem.xl, self.problem.xu, self.nu).fit(X, Y)
+        self.fitted = True
+
+
+class _OracleAcquisition:
+    def __init__(self, surrogate, kind):
+        self.s, self.kind, self.fitted = surrogate, kind, False
+
+    def fit(self, X, Y):
+        self.n_sample, self.y_min, self.fitted = len(X), np.min(Y, axis=0), True
+
+    def evaluate(self, X, dtype='continuous', gradient=False, hessian=False):
+        from oracle import gp_oracle as go
+        need_std = self.kind != "identity"
+        val = self.s.orc.evaluate(np.atleast_2d(X), std=need_std, gradient=gradient, hessian=hessian, var_form="kinv")
+        return go.acquisition(self.kind, val, gradient, hessian, n_sample=self.n_sample, y_min=self.y_min)
+
+
+class _OracleHVI:
+    def select(self, X_candidate, Y_candidate, X, Y, batch_size):
+        from oracle import moo_oracle as mo
+        return X_candidate[mo.hvi_select(Y_candidate, Y, batch_size)]
+
+
+def _zdt1(X):
+    f1 = X[:, 0]
+    g = 1 + 9.0 / (X.shape[1] - 1) * X[:, 1:].sum(1)
+    return np.stack([f1, g * (1 - np.sqrt(f1 / g))], 1)
+
+
+def _dtlz2(X, m=3):
+    g = ((X[:, m - 1:] - 0.5) ** 2).sum(1)
+    F = []
+    for i in range(m):
+        f = 1 + g
+        f = f * np.prod(np.cos(X[:, :m - 1 - i] * np.pi / 2.0), axis=1)
+        if i > 0:
+            f = f * np.sin(X[:, m - 1 - i] * np.pi / 2.0)
+        F.append(f)
+    return np.stack(F, 1)
+
+
+def run_mobo_mode(args):
+    """MOBO iteration wall time: fit + acquisition.fit + NSGA-II solve + HVI select per iteration on the
+    BASELINE configs c1 (ZDT1 d=6 m=2, identity acquisition, pop 200 x 200 generations, batch 10) and c2 (DTLZ2 d=10 m=3,
+    EI, pop 1000, batch 20): B200 path vs the CPU port with the same solver code and seeds."""
+    import random
+    from autooed_b200 import (ExpectedImprovement, GaussianProcess, HypervolumeImprovement, Identity)
+    from autooed_b200.mobo import MOBO
+    from autooed_b200.problem import SimpleProblem
+    from autooed_b200.solver import NSGA2
+    from autooed_b200.solver.nsga2 import lhs
+    from autooed_b200.utils.pareto import calc_hypervolume
+    from oracle import moo_oracle as mo
+    ctx, threads = blas_threads()
+    configs = [dict(name="c1", f=_zdt1, d=6, m=2, nu=1, acq="identity", pop=200, gens=200, batch=10, n_init=20,
+                    iters=args.mobo_iters, cpu_iters=min(args.mobo_iters, 3)),
+               dict(name="c2", f=lambda X: _dtlz2(X, 3), d=10, m=3, nu=1, acq="ei", pop=1000, gens=200, batch=20, n_init=30,
+                    iters=max(2, args.mobo_iters // 4), cpu_iters=1)]
+    for c in configs:
+        prob = SimpleProblem(c["d"], c["m"])
+        for arm in ("b200", "cpu_port"):
+            np.random.seed(0)
+            random.seed(0)
+            X = lhs(c["d"], c["n_init"])
+            Y = c["f"](X)
+            if arm == "b200":
+                sur = GaussianProcess(prob, nu=c["nu"])
+                acq = (Identity if c["acq"] == "identity" else ExpectedImprovement)(sur)
+                opt = MOBO(prob, sur, acq, NSGA2(prob, n_gen=c["gens"], pop_size=c["pop"]), HypervolumeImprovement(sur))
+                n_it = c["iters"]
+            else:
+                sur = _OracleSurrogate(prob, c["nu"])
+                acq = _OracleAcquisition(sur, c["acq"])
+                opt = MOBO(prob, sur, acq, NSGA2(prob, n_gen=c["gens"], pop_size=c["pop"], rank_fn=mo.pareto_rank), _OracleHVI())
+                n_it = c["cpu_iters"]
+            times = []
+            for it in range(n_it):
+                t0 = time.perf_counter()
+                if arm == "cpu_port":
+                    with ctx:
+                        Xn = opt.optimize(X, Y, None, c["batch"])
+                else:
+                    Xn = opt.optimize(X, Y, None, c["batch"])
+                times.append(time.perf_counter() - t0)
+                X, Y = np.vstack([X, Xn]), np.vstack([Y, c["f"](Xn)])
+            ref = np.max(c["f"](lhs(c["d"], 200)), axis=0) * 1.1
+            hv = mo.hypervolume(Y, ref) if arm == "cpu_port" else calc_hypervolume(Y, ref)
+            print(json.dumps({"mode": "mobo", "config": c["name"], "arm": arm, "acquisition": c["acq"], "pop": c["pop"],
+                              "generations": c["gens"], "batch": c["batch"], "iterations": n_it, "n_final": len(X),
+                              "s_per_iteration": float(np.mean(times)), "s_first": times[0], "s_last": times[-1],
+                              "hypervolume_of_evaluated_set": hv, "cpu_threads": threads if arm == "cpu_port" else None}),
+                  flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -302,7 +479,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU per step (default 2^20)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sample budget per step")
+    ap.add_argument("--mode", default="evals", choices=["evals", "fit", "mobo"],
+                    help="evals = the contract line (default); fit / mobo = secondary measurements, one JSON line each")
+    ap.add_argument("--mobo-iters", type=int, default=20)
     args = ap.parse_args()
+    if args.mode == "fit":
+        return run_fit_mode(args)
+    if args.mode == "mobo":
+        return run_mobo_mode(args)
     if args.impl == "reference":
         run_reference(args)
     else:
