@@ -7,7 +7,8 @@ All numerics run in libaoed_b200.so (hand-written CUDA, C ABI in include/aoed_b2
 from autooed_b200.surrogate_model import GaussianProcess
 from autooed_b200.acquisition import Identity, UpperConfidenceBound, ExpectedImprovement, ProbabilityOfImprovement
 from autooed_b200.selection import HypervolumeImprovement
-from autooed_b200.factory import (get_surrogate_model, get_acquisition, get_selection, init_surrogate_model,
-                                  init_acquisition, init_selection)
+from autooed_b200.solver import NSGA2
+from autooed_b200.factory import (get_surrogate_model, get_acquisition, get_selection, get_solver, init_surrogate_model,
+                                  init_acquisition, init_selection, init_solver)
 
 __version__ = "0.1.0"

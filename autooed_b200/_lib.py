@@ -10,7 +10,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libaoed_b200.so")
+LIB_PATH = os.environ.get("AOED_LIB") or os.path.join(_HERE, "lib", "libaoed_b200.so")  # AOED_LIB: tuning experiments
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOT_PD, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3, -4, -5

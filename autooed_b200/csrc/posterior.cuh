@@ -38,8 +38,15 @@ struct XcovArgs {
     int N, Npad, ldc, JS, jchunk;
 };
 
+#ifndef AOED_XCOV_MINBLOCKS
+#define AOED_XCOV_MINBLOCKS 2
+#endif
+#ifndef AOED_XCOV_UNROLL
+#define AOED_XCOV_UNROLL 1
+#endif
+
 template <int NU, int DP, bool GRAD>
-__global__ void __launch_bounds__(XC_THREADS) xcov_kernel(XcovArgs p) {
+__global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(XcovArgs p) {
     __shared__ __align__(16) double ts[XC_JT][DP];
     __shared__ double al[XC_JT];
     const int tid = threadIdx.x;
@@ -70,6 +77,39 @@ __global__ void __launch_bounds__(XC_THREADS) xcov_kernel(XcovArgs p) {
         for (int i = tid; i < nj * DP; i += XC_THREADS) (&ts[0][0])[i] = Ts[int64_t(j0) * DP + i];
         if (tid < nj) al[tid] = alpha[j0 + tid];
         __syncthreads();
+#if AOED_XCOV_UNROLL == 1
+        for (int jj = 0; jj < nj; ++jj) {
+            double r2 = 0.0, r2b = 0.0;
+#pragma unroll
+            for (int k = 0; k < DP; k += 2) {
+                const double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
+                const double d0 = xs[k] - t.x, d1 = xs[k + 1] - t.y;
+                r2 = fma(d0, d0, r2);
+                r2b = fma(d1, d1, r2b);
+            }
+            r2 += r2b;
+            const double r = sqrt(r2);
+            double phi, gor;
+            kernel_profile<NU>(r, r2, phi, gor);
+            const double kv = fma(c1, phi, c2);
+            const double a = al[jj];
+            mu = fma(kv, a, mu);
+            if (KsT) KsT[int64_t(j0 + jj) * p.ldc + c] = kv;
+            if (GRAD) {
+                const double w = c1 * gor;
+                if (Gr) Gr[int64_t(j0 + jj) * p.ldc + c] = w;
+                const double wa = w * a;
+                s0 += wa;
+#pragma unroll
+                for (int k = 0; k < DP; k += 2) {
+                    const double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
+                    sk[k] = fma(wa, t.x, sk[k]);
+                    sk[k + 1] = fma(wa, t.y, sk[k + 1]);
+                }
+            }
+        }
+    }
+#else
         // two training points per iteration with split distance accumulators: the serial FMA -> sqrt -> exp chains of
         // independent points overlap (the kernel is FP64-latency bound at 4-8 warps per SM)
         for (int jj = 0; jj < nj; jj += 2) {
@@ -121,6 +161,7 @@ __global__ void __launch_bounds__(XC_THREADS) xcov_kernel(XcovArgs p) {
             }
         }
     }
+#endif
     double* __restrict__ part = p.part + (int64_t(o) * p.JS + js) * (2 + DP) * p.ldc + c;
     part[0] = mu;
     if (GRAD) {

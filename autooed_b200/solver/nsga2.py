@@ -11,6 +11,7 @@ acquisition evaluation inside the loop is the parity-tested device call.
 Every generation costs one batched `problem.evaluate` (pop_size rows) — the work the B200 path accelerates — plus
 O(pop^2) host bookkeeping; non-dominated sorting runs on the GPU when `rank_fn` is the default."""
 import numpy as np
+from scipy.spatial.distance import cdist
 
 from autooed_b200.solver.base import Solver
 
@@ -101,10 +102,8 @@ class NSGA2Algorithm:
         """Offspring equal (squared distance <= eps) to a population member or an earlier offspring are discarded."""
         keep = np.ones(len(X), dtype=bool)
         if len(others):
-            d2 = ((X[:, None, :] - others[None, :, :]) ** 2).sum(-1)
-            keep &= ~(d2 <= eps).any(axis=1)
-        d2 = ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1)
-        keep &= ~np.triu(d2 <= eps, 1).any(axis=0)
+            keep &= ~(cdist(X, others, 'sqeuclidean') <= eps).any(axis=1)
+        keep &= ~np.triu(cdist(X, X, 'sqeuclidean') <= eps, 1).any(axis=0)
         return X[keep]
 
     # -- survival --------------------------------------------------------------------------------------------------

@@ -452,6 +452,24 @@ def run_mobo_mode(args):
                 acq = _OracleAcquisition(sur, c["acq"])
                 opt = MOBO(prob, sur, acq, NSGA2(prob, n_gen=c["gens"], pop_size=c["pop"], rank_fn=mo.pareto_rank), _OracleHVI())
                 n_it = c["cpu_iters"]
+            # where the iteration goes: surrogate fit, acquisition calls + non-dominated sorting inside the solver, selection
+            split = {"fit": 0.0, "acq_evaluate": 0.0, "rank": 0.0, "select": 0.0}
+
+            def timed(obj, name, key):
+                fn = getattr(obj, name)
+
+                def wrapper(*a, **k):
+                    t0 = time.perf_counter()
+                    try:
+                        return fn(*a, **k)
+                    finally:
+                        split[key] += time.perf_counter() - t0
+                setattr(obj, name, wrapper)
+
+            timed(sur, "fit", "fit")
+            timed(acq, "evaluate", "acq_evaluate")
+            timed(opt.solver.algo, "rank_fn", "rank")
+            timed(opt.selection, "select", "select")
             times = []
             for it in range(n_it):
                 t0 = time.perf_counter()
@@ -467,6 +485,7 @@ def run_mobo_mode(args):
             print(json.dumps({"mode": "mobo", "config": c["name"], "arm": arm, "acquisition": c["acq"], "pop": c["pop"],
                               "generations": c["gens"], "batch": c["batch"], "iterations": n_it, "n_final": len(X),
                               "s_per_iteration": float(np.mean(times)), "s_first": times[0], "s_last": times[-1],
+                              "s_per_iteration_split": {k: v / n_it for k, v in split.items()},
                               "hypervolume_of_evaluated_set": hv, "cpu_threads": threads if arm == "cpu_port" else None}),
                   flush=True)
 
