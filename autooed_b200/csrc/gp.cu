@@ -525,7 +525,7 @@ int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool 
     e.F = out.F; e.S = out.S; e.dF = out.dF; e.dS = out.dS; e.A = out.A; e.dA = out.dA;
     e.rows = rows; e.m = m; e.d = gp->d; e.DP = DP; e.ldc = ldc; e.JS = JS1; e.JS2 = JS2; e.mTiles = gp->mTiles * gp->ssf;
     e.std = want_std; e.grad = want_grad; e.acq = acq;
-    epilogue_kernel<<<dim3(unsigned((rows + EPI_THREADS - 1) / EPI_THREADS), m), EPI_THREADS, 0, s>>>(e);
+    epilogue_kernel<<<dim3(unsigned((rows + EPI_CX - 1) / EPI_CX), m), dim3(EPI_CX, EPI_KY), 0, s>>>(e);
     gp->n_launches++;
     CU(cudaGetLastError());
     return AOED_OK;

@@ -276,52 +276,82 @@ __device__ __forceinline__ void acq_first_order(const AcqDev& acq, int o, double
     }
 }
 
-constexpr int EPI_THREADS = 64;  // small CTAs: the grid is only rows/64 x m, spread it over all SMs
+constexpr int EPI_CX = 32;  // candidates per CTA
+constexpr int EPI_KY = 8;   // threads per candidate: the partial-sum reads (~470 per candidate and objective) are split
+                            // over them, otherwise the few thousand candidates of a chunk leave the GPU latency bound
 
-__global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(EpilogueArgs p) {
-    const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+__global__ void __launch_bounds__(EPI_CX * EPI_KY) epilogue_kernel(EpilogueArgs p) {
+    __shared__ double sc[4][EPI_CX];  // mu, sum of squares, s0, t0 per candidate
+    const int cx = threadIdx.x, ky = threadIdx.y;
+    const int64_t c = blockIdx.x * int64_t(EPI_CX) + cx;
     const int o = blockIdx.y;
-    if (c >= p.rows) return;
+    const bool live = c < p.rows;
+    const int64_t cc = live ? c : 0;  // dead lanes read a valid column and store nothing
     const ModelDev md = p.model[o];
     const int ldc = p.ldc, DP = p.DP;
     const int64_t pstride = int64_t(2 + DP) * ldc;
-    const double* part = p.part + int64_t(o) * p.JS * pstride + c;
-    double mu = 0.0;
+    const double* part = p.part + int64_t(o) * p.JS * pstride + cc;
+    const int64_t p2stride = int64_t(1 + DP) * ldc;
+    const double* part2 = p.part2 + int64_t(o) * p.JS2 * p2stride + cc;
+    // ---- phase 1: the four per-candidate scalars, one per ky (the sum of squares is shared by ky = 1, 4..7) ----
+    if (ky == 0) {
+        double mu = 0.0;
 #pragma unroll 4
-    for (int js = 0; js < p.JS; ++js) mu += part[js * pstride];
+        for (int js = 0; js < p.JS; ++js) mu += part[js * pstride];
+        sc[0][cx] = mu;
+    } else if (ky == 2) {
+        double s0 = 0.0;
+        if (p.grad) {
+#pragma unroll 4
+            for (int js = 0; js < p.JS; ++js) s0 += part[js * pstride + ldc];
+        }
+        sc[2][cx] = s0;
+    } else if (ky == 3) {
+        double t0 = 0.0;
+        if (p.grad && p.std) {
+#pragma unroll 4
+            for (int js = 0; js < p.JS2; ++js) t0 += part2[js * p2stride];
+        }
+        sc[3][cx] = t0;
+    }
+    __shared__ double ssq[5][EPI_CX];
+    if (ky == 1 || ky >= 4) {
+        const int slot = ky == 1 ? 0 : ky - 3;  // 5 readers, fixed tile ranges -> deterministic summation order
+        double acc = 0.0;
+        if (p.std) {
+            const double* ss = p.sumsq + int64_t(o) * p.mTiles * ldc + cc;
+            const int per = (p.mTiles + 4) / 5;
+            const int t1 = min(p.mTiles, (slot + 1) * per);
+#pragma unroll 4
+            for (int t = slot * per; t < t1; ++t) acc += ss[int64_t(t) * ldc];
+        }
+        ssq[slot][cx] = acc;
+    }
+    __syncthreads();
+    const double mu = sc[0][cx];
     double sd = 0.0;
     if (p.std) {
-        double acc = 0.0;
-        const double* ss = p.sumsq + int64_t(o) * p.mTiles * ldc + c;
-#pragma unroll 8
-        for (int t = 0; t < p.mTiles; ++t) acc += ss[int64_t(t) * ldc];
+        const double acc = (((ssq[0][cx] + ssq[1][cx]) + ssq[2][cx]) + ssq[3][cx]) + ssq[4][cx];
         double var = (md.c1 + md.c2) - acc;  // kernel_.diag(X) - |L^-1 k*|^2   (gp.py:159-161)
         if (var < 0.0) var = 0.0;            // gp.py:163-165
         sd = sqrt(var);
     }
     const double F = fma(mu, md.y_scale, md.y_mean);  // base.py:106
     const double S = sd * md.y_scale;                 // base.py:108
-    const int64_t io = c * p.m + o;
-    if (p.F) p.F[io] = F;
-    if (p.S && p.std) p.S[io] = S;
+    const int64_t io = cc * p.m + o;
     double aval = 0.0, a_mu = 1.0, a_sd = 0.0;
-    if (p.acq.kind != 0) {
-        acq_first_order(p.acq, o, F, S, aval, a_mu, a_sd);
-        if (p.A) p.A[io] = aval;
+    if (p.acq.kind != 0) acq_first_order(p.acq, o, F, S, aval, a_mu, a_sd);
+    if (ky == 0 && live) {
+        if (p.F) p.F[io] = F;
+        if (p.S && p.std) p.S[io] = S;
+        if (p.A && p.acq.kind != 0) p.A[io] = aval;
     }
     if (!p.grad) return;
-    double s0 = 0.0, t0 = 0.0;
-#pragma unroll 4
-    for (int js = 0; js < p.JS; ++js) s0 += part[js * pstride + ldc];
-    const int64_t p2stride = int64_t(1 + DP) * ldc;
-    const double* part2 = p.part2 + int64_t(o) * p.JS2 * p2stride + c;
-    if (p.std) {
-#pragma unroll 4
-        for (int js = 0; js < p.JS2; ++js) t0 += part2[js * p2stride];
-    }
-    for (int k = 0; k < p.d; ++k) {
+    // ---- phase 2: dimensions k = ky, ky + 8, ... ----
+    const double s0 = sc[2][cx], t0 = sc[3][cx];
+    for (int k = ky; k < p.d; k += EPI_KY) {
         const double ell = p.ell[o * DP + k];
-        const double xs = p.XT[int64_t(k) * ldc + c] / ell;
+        const double xs = p.XT[int64_t(k) * ldc + cc] / ell;
         double sk = 0.0;
 #pragma unroll 4
         for (int js = 0; js < p.JS; ++js) sk += part[js * pstride + int64_t(2 + k) * ldc];
@@ -335,10 +365,12 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(EpilogueArgs p) {
             const double dvar = -2.0 * (t0 * xs - tk) / ell;  // gp.py:201-205
             dSk = 0.5 * safe_div(dvar, sd) * md.y_scale;      // gp.py:206, base.py:109
         }
-        const int64_t ig = io * p.d + k;
-        if (p.dF) p.dF[ig] = dFk;
-        if (p.dS && p.std) p.dS[ig] = dSk;
-        if (p.dA && p.acq.kind != 0) p.dA[ig] = a_mu * dFk + a_sd * dSk;
+        if (live) {
+            const int64_t ig = io * p.d + k;
+            if (p.dF) p.dF[ig] = dFk;
+            if (p.dS && p.std) p.dS[ig] = dSk;
+            if (p.dA && p.acq.kind != 0) p.dA[ig] = a_mu * dFk + a_sd * dSk;
+        }
     }
 }
 
