@@ -11,7 +11,7 @@
 // Phases (all in shared memory, CTA-wide barriers in between):
 //   1  K = c1 phi(r) + c2 (+ jitter on the diagonal), lower triangle only
 //   2  in-place right-looking Cholesky  K = L L^T          (a non-positive pivot => lml = -inf, grad = 0, _gpr.py:589-593)
-//   3  in-place inverse of L (column sweep from the right, LAPACK dtrti2 order)
+//   3  in-place inverse of L (right-looking rank-1 updates, no reductions)
 //   4  z = L^-1 y, alpha = L^-T z, lml = -1/2 z.z - sum log L_ii - N/2 log 2 pi
 //   5  grad_k = 1/2 sum_ij (alpha_i alpha_j - (L^-T L^-1)_ij) dK_ij/dtheta_k with K^-1_ij formed on the fly
 #pragma once
@@ -31,6 +31,7 @@ struct LmlSmallArgs {
     const int* obj;        // [B]
     double* res;           // [B][1 + d + 2]: lml, grad[c1, l_1..l_d, c2]
     int N, Npad, d, want_grad;
+    long long* clk;        // optional [B][8] phase timestamps (clock64) for tuning, or nullptr
 };
 
 inline size_t lml_small_smem(int N, int DP) {
@@ -62,6 +63,9 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_small_kernel(LmlSmallArgs p
     for (int i = tid; i < N; i += FS_THREADS) yv[i] = y[i];
     __syncthreads();
 
+#define FS_STAMP(idx)                                                  \
+    if (p.clk != nullptr && tid == 0) p.clk[int64_t(b) * 8 + (idx)] = clock64();
+    FS_STAMP(0)
     // ---- 1: kernel matrix -------------------------------------------------------------------------------------
     for (int i = warp; i < N; i += FS_WARPS) {
         const double* xi = p.X + int64_t(i) * d;
@@ -79,17 +83,17 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_small_kernel(LmlSmallArgs p
     }
     __syncthreads();
 
+    FS_STAMP(1)
     // ---- 2: Cholesky -------------------------------------------------------------------------------------------
-    double logdet = 0.0;
     for (int k = 0; k < N; ++k) {
         const double dkk = Lp[tri(k) + k];
         if (!(dkk > 0.0)) {  // also catches NaN
             if (tid == 0) s_fail = 1;
             break;  // uniform: every thread reads the same value
         }
-        const double piv = sqrt(dkk);
-        logdet += log(piv);
-        const double ipiv = 1.0 / piv;
+        // every thread needs 1/pivot: rsqrt (one MUFU + Newton steps) instead of sqrt + divide; log|L| is summed after the loop
+        const double ipiv = rsqrt(dkk);
+        const double piv = dkk * ipiv;
         __syncthreads();  // everyone has read the pivot
         for (int i = k + 1 + tid; i < N; i += FS_THREADS) {
             const double v = Lp[tri(i) + k] * ipiv;
@@ -107,30 +111,44 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_small_kernel(LmlSmallArgs p
     }
     __syncthreads();
     double* out = p.res + int64_t(b) * (d + 3);
+    double logdet = 0.0;  // complete in every lane of warp 0 only (the one consumer)
+    if (warp == 0 && !s_fail) {
+        for (int k = lane; k < N; k += 32) logdet += log(Lp[tri(k) + k]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) logdet += __shfl_xor_sync(0xffffffffu, logdet, off);
+    }
     if (s_fail) {
         if (tid == 0) out[0] = -INFINITY;
         if (tid < d + 2) out[1 + tid] = 0.0;
         return;
     }
 
+    FS_STAMP(2)
     // ---- 3: L <- L^-1 in place ---------------------------------------------------------------------------------
-    for (int j = N - 1; j >= 0; --j) {
-        const double ajj = 1.0 / Lp[tri(j) + j];
-        for (int i = j + 1 + tid; i < N; i += FS_THREADS) col[i] = Lp[tri(i) + j];
-        __syncthreads();
-        // x_i = -ajj * sum_{k=j+1..i} Linv[i][k] * L[k][j]   (rows i of the already inverted trailing block)
-        for (int i = j + 1 + warp; i < N; i += FS_WARPS) {
-            const double* row = Lp + tri(i);
-            double s = 0.0;
-            for (int k = j + 1 + lane; k <= i; k += 32) s = fma(row[k], col[k], s);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) Lp[tri(i) + j] = -ajj * s;
+    // Right-looking: storage holds R = I - (partial products) below/left of the pivot row; step k finalises row k of
+    // X = L^-1 (X[k][j] = R[k][j] / L_kk) and applies the rank-1 update R[i][j] -= L[i][k] X[k][j] to the rectangle
+    // i > k, j <= k.  Entry (i, k) turns from L[i][k] into R[i][k] at step k, so the inversion is in place, and every
+    // update is an independent fused multiply-add (no reductions).
+    double* rowb = zv;  // [N] scratch: row k of X (zv is not used before phase 4)
+    for (int k = 0; k < N; ++k) {
+        const double ikk = 1.0 / Lp[tri(k) + k];
+        __syncthreads();  // everyone has read the pivot; the previous step's updates are complete
+        for (int i = k + 1 + tid; i < N; i += FS_THREADS) col[i] = Lp[tri(i) + k];
+        for (int j = tid; j <= k; j += FS_THREADS) {
+            const double x = (j == k) ? ikk : Lp[tri(k) + j] * ikk;
+            Lp[tri(k) + j] = x;
+            rowb[j] = x;
         }
-        if (tid == 0) Lp[tri(j) + j] = ajj;
         __syncthreads();
+        for (int i = k + 1 + warp; i < N; i += FS_WARPS) {
+            const double ci = col[i];
+            double* row = Lp + tri(i);
+            for (int j = lane; j <= k; j += 32) row[j] = fma(-ci, rowb[j], (j == k) ? 0.0 : row[j]);
+        }
     }
+    __syncthreads();
 
+    FS_STAMP(3)
     // ---- 4: z = L^-1 y, alpha = L^-T z ---------------------------------------------------------------------------
     for (int i = warp; i < N; i += FS_WARPS) {
         const double* row = Lp + tri(i);
@@ -156,6 +174,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_small_kernel(LmlSmallArgs p
         if (lane == 0) out[0] = -0.5 * q - logdet - 0.5 * N * 1.8378770664093453;  // log(2 pi)   (_gpr.py:601-616)
     }
     __syncthreads();
+    FS_STAMP(4)
     if (!p.want_grad) return;
 
     // ---- 5: gradient ---------------------------------------------------------------------------------------------
@@ -207,6 +226,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_small_kernel(LmlSmallArgs p
         else if (tid == DP + 1) out[1 + d + 1] = s;
         else if (tid - 1 < d) out[1 + tid] = s;
     }
+    FS_STAMP(5)
+#undef FS_STAMP
 }
 
 }  // namespace aoed

@@ -1052,7 +1052,22 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
         LmlSmallArgs a;
         a.X = gp->dX; a.Y = gp->dY; a.theta = gp->dThetaB; a.obj = gp->dObjB; a.res = gp->dResB;
         a.N = N; a.Npad = Npad; a.d = d; a.want_grad = want_grad ? 1 : 0;
+        a.clk = nullptr;
+        static const bool stamp = getenv("AOED_FIT_STAMP") != nullptr;  // tuning aid: prints per-phase cycles of problem 0
+        long long* dclk = nullptr;
+        if (stamp) {
+            CU(cudaMalloc(&dclk, size_t(n_prob) * 8 * sizeof(long long)));
+            a.clk = dclk;
+        }
         CHK(launch_lml_small(gp->nu, DP, a, n_prob, s0));
+        if (stamp) {
+            long long h[8];
+            CU(cudaMemcpyAsync(h, dclk, sizeof(h), cudaMemcpyDeviceToHost, s0));
+            CU(cudaStreamSynchronize(s0));
+            fprintf(stderr, "lml_small N=%d cycles: kmat %lld chol %lld inv %lld alpha %lld grad %lld\n", N, h[1] - h[0],
+                    h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
+            cudaFree(dclk);
+        }
         gp->n_launches++;
         gp->n_fit_small += n_prob;
     } else {

@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <cfloat>
 #include <numeric>
 #include <string>
@@ -105,6 +107,96 @@ __global__ void rank_update_kernel(int64_t n, const uint8_t* dominated, uint8_t*
     } else {
         atomicAdd(remaining, 1ull);
     }
+}
+
+// Whole non-dominated sort in ONE CTA for populations that fit in shared memory (the NSGA-II regime, n <= 4096):
+// domination counts, then front peeling with the counts decremented by the members of each peeled front — no host
+// round trip per front.  Same semantics as the multi-launch path below (rank = front number, pymoo NonDominatedSorting).
+constexpr int RS_THREADS = 1024;
+constexpr int RS_MAX_N = 4096;
+
+template <int M>
+__global__ void __launch_bounds__(RS_THREADS) rank_small_kernel(const double* __restrict__ YT, int n, int32_t* __restrict__ rank_out) {
+    extern __shared__ double rs_smem[];
+    double* Y = rs_smem;                                   // [M][n]
+    int* cnt = reinterpret_cast<int*>(Y + size_t(M) * n);  // [n] number of not-yet-peeled points dominating i
+    int* rk = cnt + n;                                     // [n]
+    int* front = rk + n;                                   // [n] compacted current front
+    __shared__ int n_front, n_left;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < M * n; i += RS_THREADS) Y[i] = YT[i];
+    if (tid == 0) n_left = n;
+    __syncthreads();
+    for (int i = tid; i < n; i += RS_THREADS) {
+        double yi[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) yi[k] = Y[k * n + i];
+        int c = 0;
+        for (int j = 0; j < n; ++j) {
+            bool le = true, lt = false;
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                const double v = Y[k * n + j];
+                le = le && (v <= yi[k]);
+                lt = lt || (v < yi[k]);
+            }
+            c += (le && lt) ? 1 : 0;
+        }
+        cnt[i] = c;
+        rk[i] = -1;
+    }
+    __syncthreads();
+    for (int r = 0; n_left > 0; ++r) {
+        if (tid == 0) n_front = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += RS_THREADS)
+            if (rk[i] < 0 && cnt[i] == 0) {
+                rk[i] = r;
+                front[atomicAdd(&n_front, 1)] = i;
+            }
+        __syncthreads();
+        const int nf = n_front;
+        if (nf == 0) break;  // cannot happen for finite inputs (a minimal element always exists); NaN rows stay at -1
+        for (int q = tid; q < n; q += RS_THREADS) {
+            if (rk[q] >= 0) continue;
+            double yq[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) yq[k] = Y[k * n + q];
+            int dec = 0;
+            for (int t = 0; t < nf; ++t) {
+                const int pidx = front[t];
+                bool le = true, lt = false;
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    const double v = Y[k * n + pidx];
+                    le = le && (v <= yq[k]);
+                    lt = lt || (v < yq[k]);
+                }
+                dec += (le && lt) ? 1 : 0;
+            }
+            cnt[q] -= dec;
+        }
+        __syncthreads();
+        if (tid == 0) n_left -= nf;
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += RS_THREADS) rank_out[i] = rk[i];
+}
+
+int launch_rank_small(int m, const double* YT, int n, int32_t* rank, cudaStream_t s) {
+    const size_t sm = size_t(m) * n * sizeof(double) + 3 * size_t(n) * sizeof(int);
+#define RS_CASE(MM)                                                                                                  \
+    case MM:                                                                                                         \
+        MCU(cudaFuncSetAttribute(rank_small_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));      \
+        rank_small_kernel<MM><<<1, RS_THREADS, sm, s>>>(YT, n, rank);                                                \
+        break;
+    switch (m) {
+        RS_CASE(1) RS_CASE(2) RS_CASE(3) RS_CASE(4) RS_CASE(5) RS_CASE(6) RS_CASE(7) RS_CASE(8)
+        default: return mfail(AOED_ERR_UNSUPPORTED, "n_obj > 8 is not supported");
+    }
+#undef RS_CASE
+    MCU(cudaGetLastError());
+    return AOED_OK;
 }
 
 // ---- exclusive hypervolume -----------------------------------------------------------------------------
@@ -332,6 +424,20 @@ int aoed_pareto_rank(int device, int64_t n, int m, const double* h_Y, int32_t* h
     aoed::DeviceGuard guard_(device);
     MCU(guard_.err);
     std::vector<double> yt = to_objective_major(h_Y, n, m);
+    const char* force = getenv("AOED_RANK_PATH");  // "multi" forces the multi-launch path (tests)
+    if (!(force && strcmp(force, "multi") == 0) && n <= RS_MAX_N &&
+        size_t(m) * n * sizeof(double) + 3 * size_t(n) * sizeof(int) <= 200 * 1024) {
+        // one launch, one allocation: the call is latency bound (it runs once per NSGA-II generation)
+        Buf d;
+        const size_t ybytes = yt.size() * sizeof(double);
+        MCU(cudaMalloc(&d.p, ybytes + size_t(n) * sizeof(int32_t)));
+        MCU(cudaMemcpy(d.p, yt.data(), ybytes, cudaMemcpyHostToDevice));
+        int32_t* drank = reinterpret_cast<int32_t*>(static_cast<char*>(d.p) + ybytes);
+        int rc = launch_rank_small(m, d.as<double>(), int(n), drank, nullptr);
+        if (rc != AOED_OK) return rc;
+        MCU(cudaMemcpy(h_rank, drank, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        return AOED_OK;
+    }
     Buf dY, dDom, dAlive, dRank, dRem;
     MCU(cudaMalloc(&dY.p, yt.size() * sizeof(double)));
     MCU(cudaMalloc(&dDom.p, size_t(n)));

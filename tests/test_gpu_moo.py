@@ -22,6 +22,20 @@ def test_pareto_mask_and_front(n, m):
     assert np.array_equal(pareto.pareto_rank(Y), mo.pareto_rank(Y))
 
 
+@pytest.mark.parametrize("path", ["single-cta", "multi"])
+def test_pareto_rank_paths(path, monkeypatch):
+    """Both device paths of the non-dominated sort (one-CTA shared-memory kernel, multi-launch peeling) on a population
+    with many fronts, ties and duplicates."""
+    from autooed_b200.utils import pareto
+    if path == "multi":
+        monkeypatch.setenv("AOED_RANK_PATH", "multi")
+    rng = np.random.default_rng(3)
+    Y = np.round(rng.random((700, 3)), 1)
+    Y[:50] = Y[50:100]
+    r = pareto.pareto_rank(Y)
+    assert np.array_equal(r, mo.pareto_rank(Y)) and r.max() > 5
+
+
 def test_pareto_empty():
     from autooed_b200.utils import pareto
     assert len(pareto.find_pareto_front(np.empty((0, 2)))) == 0
