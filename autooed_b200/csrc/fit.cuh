@@ -149,6 +149,22 @@ __global__ void __launch_bounds__(256) lml_grad_reduce_kernel(const double* __re
     else if (k - 1 < d) res[1 + k] = s;
 }
 
+// y_out[i] = sum_j A[i][j] x[j] over the stored triangle of a row-major matrix: LOWER (j <= i) or UPPER (j >= i).
+// One warp per row; used for z = L^-1 y and alpha = L^-T z of the blocked LML path.
+template <bool UPPER>
+__global__ void __launch_bounds__(256) tri_matvec_kernel(const double* __restrict__ A, const double* __restrict__ x, int N, int ld,
+                                                         double* __restrict__ y_out) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= N) return;
+    const double* a = A + int64_t(row) * ld;
+    const int j0 = UPPER ? row : 0, j1 = UPPER ? N : row + 1;
+    double s = 0.0;
+    for (int j = j0 + lane; j < j1; j += 32) s = fma(a[j], x[j], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) y_out[row] = s;
+}
+
 // Ts = X / l (padded to DP), c1c2 = exp(theta[0]), exp(theta[d+1]) for one hyper-parameter vector (device-side, no host sync)
 __global__ void theta_prep_kernel(const double* __restrict__ X, const double* __restrict__ theta, int N, int Npad, int d,
                                   int DP, double* __restrict__ Ts, double* __restrict__ c1c2) {
@@ -163,6 +179,7 @@ __global__ void theta_prep_kernel(const double* __restrict__ X, const double* __
 }
 
 // res[0] = -1/2 y.alpha - sum log L_ii - N/2 log 2 pi   (_gpr.py:601-616); -inf when potrf reported a non-PD matrix
+// quad_a . quad_b is y . alpha (sklearn's form) or z . z with z = L^-1 y (same number, better conditioned)
 __global__ void __launch_bounds__(256) lml_value_kernel(const double* __restrict__ y, const double* __restrict__ alpha,
                                                         const double* __restrict__ Lfac, int N, int Npad, const int* info,
                                                         double* res) {

@@ -26,7 +26,7 @@ METRIC = "gp_posterior_grad_candidate_evals_per_sec"
 UNIT = "evals/s"
 WORKLOAD = dict(workload="c4: synthetic GP N=2000 d=20 n_obj=3, Matern-5/2, UCB value+gradient over 2^20 candidates per GPU",
                 n_train=2000, n_var=20, n_obj=3, nu=5, acquisition="ucb", candidates_per_gpu=1 << 20,
-                l2_policy="working set per step (K*, W, V, Gr slabs: 805 MB per chunk; outputs 528 MB) exceeds the 126 MB L2")
+                l2_policy="inputs larger than L2: every chunk of 16384 candidates streams 3.2 GB of K*, W, V, g/r slabs (126 MB L2), outputs 528 MB per step")
 
 
 def make_problem(n_train, d, m, seed=0):
@@ -267,7 +267,7 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": kname,
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
-                    "algorithmic_bytes_per_launch": 8.0 * m * (0.5 * N * N + 2.0 * N * min(C, 4096)),
+                    "algorithmic_bytes_per_launch": 8.0 * m * (0.5 * N * N + 2.0 * N * min(C, 16384)),
                     "peak_source": "cuBLAS DGEMM fp64 8192^3 measured live in this run (MEASURED_PEAKS.json holds HBM and bf16 "
                                    "only; FP64 DMMA issue peak measured at 37.2 TFLOP/s, profiles/fp64_pipe_probe_r01.json)",
                     "flops_per_launch": cnt["trmm_flops"] / max(cnt["trmm_launches"], 1),
