@@ -48,7 +48,7 @@ __device__ __forceinline__ void kernel_profile(double r, double r2, double& phi,
     } else if (NU == 5) {
         double s = kSqrt5 * r;
         double e = exp(-s);
-        phi = (1.0 + s + s * s / 3.0) * e;
+        phi = (1.0 + s + s * s * (1.0 / 3.0)) * e;  // reciprocal constant: a true divide costs ~10 FP64 instructions per pair
         g_over_r = -5.0 / 3.0 * e * (1.0 + s);
     } else {
         double e = exp(-0.5 * r2);

@@ -354,6 +354,38 @@ def run_fit_mode(args):
                           "gpu_fit_info": {k: v for k, v in gp.fit_info.items() if k != "nfev"},
                           "cpu_port_s_single_start": cpu_s, "cpu_threads": threads, "cpu_nfev": orc.nfev}), flush=True)
 
+    def hessian_calls(N, d, m, nu, C, acq_name):
+        """c3-like: the ParetoDiscovery access pattern — value + gradient + Hessian of the acquisition for a small batch."""
+        from autooed_b200 import ExpectedImprovement, Identity
+        X, Y = _fit_data(N, d, m)
+        thetas = np.stack([np.concatenate([[0.0], np.full(d, 0.3), [math.log(0.01)]]) for _ in range(m)])
+        gp = GaussianProcess(SimpleProblem(d, m), nu=nu)
+        gp.fit_fixed(X, Y, thetas)
+        acq = (Identity if acq_name == "identity" else ExpectedImprovement)(gp)
+        acq.fit(X, Y)
+        Xs = np.random.default_rng(3).random((C, d))
+        acq.evaluate(Xs, gradient=True, hessian=True)
+        reps = 20
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            acq.evaluate(Xs, gradient=True, hessian=True)
+        gpu_s = (time.perf_counter() - t0) / reps
+        orc = go.GPOracle(d, m, nu=nu).fit(X, Y, thetas=thetas)
+        n_cpu = min(C, 16)
+        with ctx:
+            t0 = time.perf_counter()
+            val = orc.evaluate(Xs[:n_cpu], std=acq_name != "identity", gradient=True, hessian=True, var_form="kinv", chunk=1)
+            go.acquisition(acq_name, val, True, True, n_sample=N, y_min=Y.min(0))
+            cpu_s = (time.perf_counter() - t0) / n_cpu
+        print(json.dumps({"mode": "fit", "what": "acquisition value+gradient+hessian call", "N": N, "d": d, "m": m, "nu": nu,
+                          "acquisition": acq_name, "rows_per_call": C, "gpu_ms_per_call": 1e3 * gpu_s,
+                          "gpu_rows_per_s": C / gpu_s, "cpu_port_ms_per_row": 1e3 * cpu_s, "cpu_threads": threads,
+                          "speedup": cpu_s * C / gpu_s}), flush=True)
+
+    hessian_calls(200, 30, 2, 5, 1, "identity")
+    hessian_calls(200, 30, 2, 5, 100, "identity")
+    hessian_calls(200, 30, 2, 5, 100, "ei")
+    hessian_calls(2000, 20, 3, 5, 100, "ei")
     lml_batches(200, 6, 2, 5, [1, 2, 16, 148, 592])
     lml_batches(500, 10, 3, 5, [3, 48])
     lml_batches(2000, 20, 3, 5, [3, 48], reps=2, cpu_calls=1)
