@@ -223,8 +223,11 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end leg (`e2e`): public API, host numpy in / host numpy out -----------------------------------
-    for _ in range(max(1, args.warmup // 2)):
-        acq.evaluate(Xs, dtype='normalized', gradient=True)
+    # warm-up keeps results alive exactly like the timed loop does (previous result still referenced while the next call
+    # runs), so that the pinned result-buffer pool reaches its steady state of two sets before timing starts
+    F = dF = None
+    for _ in range(max(2, args.warmup // 2 + 1)):
+        F, dF, _ = acq.evaluate(Xs, dtype='normalized', gradient=True)
     barrier()
     t0 = time.perf_counter()
     e0.record()
@@ -239,8 +242,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e = t.tolist()
 
-    # numerics guard: device leg and host leg agree
-    same = bool(np.allclose(dA.cpu().numpy(), F, rtol=0, atol=0))
+    # numerics guard: device leg and host leg agree (different chunk sizes => different partial-sum splits, not bitwise)
+    same = bool(np.allclose(dA.cpu().numpy(), F, rtol=1e-11, atol=1e-12))
 
     if rank == 0:
         # ---- roofline of the dominant kernel (triangular FP64 DMMA product), timed with events per launch -------
@@ -285,7 +288,7 @@ def run_ours(args):
                 "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": blas_threads()[1], "kind": "port",
                                  "sample": f"{cpu_done} candidates of the same workload in {cpu_el:.1f}s (oracle/gp_oracle.py, numpy BLAS threads unrestricted)"},
-                "clocks": clocks, "device_host_legs_identical": same}
+                "clocks": clocks, "device_host_legs_agree": same}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
