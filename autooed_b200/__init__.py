@@ -5,8 +5,9 @@
 All numerics run in libaoed_b200.so (hand-written CUDA, C ABI in include/aoed_b200.h); there is no CPU fallback.
 """
 from autooed_b200.surrogate_model import GaussianProcess
-from autooed_b200.acquisition import Identity, UpperConfidenceBound, ExpectedImprovement, ProbabilityOfImprovement
-from autooed_b200.selection import HypervolumeImprovement
+from autooed_b200.acquisition import (Identity, UpperConfidenceBound, ExpectedImprovement, ProbabilityOfImprovement,
+                                      ThompsonSampling)
+from autooed_b200.selection import HypervolumeImprovement, Uncertainty, Direct
 from autooed_b200.solver import NSGA2
 from autooed_b200.factory import (get_surrogate_model, get_acquisition, get_selection, get_solver, init_surrogate_model,
                                   init_acquisition, init_selection, init_solver)

@@ -1,14 +1,15 @@
 """Name -> class maps with the reference's factory names (`autooed/mobo/factory.py:11-22, 25-38, 74-86`), so that
 a maintainer can route 'gp' / 'ei' / 'identity' / 'pi' / 'ucb' / 'hvi' to the B200 path."""
 from autooed_b200.surrogate_model import GaussianProcess
-from autooed_b200.acquisition import Identity, UpperConfidenceBound, ExpectedImprovement, ProbabilityOfImprovement
-from autooed_b200.selection import HypervolumeImprovement
+from autooed_b200.acquisition import (Identity, UpperConfidenceBound, ExpectedImprovement, ProbabilityOfImprovement,
+                                      ThompsonSampling)
+from autooed_b200.selection import HypervolumeImprovement, Uncertainty, Direct
 from autooed_b200.solver import NSGA2
 
 _SURROGATES = {'gp': GaussianProcess}
 _ACQUISITIONS = {'ei': ExpectedImprovement, 'identity': Identity, 'pi': ProbabilityOfImprovement,
-                 'ucb': UpperConfidenceBound}
-_SELECTIONS = {'hvi': HypervolumeImprovement}
+                 'ts': ThompsonSampling, 'ucb': UpperConfidenceBound}
+_SELECTIONS = {'direct': Direct, 'hvi': HypervolumeImprovement, 'uncertainty': Uncertainty}
 _SOLVERS = {'nsga2': NSGA2}
 
 

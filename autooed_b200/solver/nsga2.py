@@ -14,14 +14,7 @@ import numpy as np
 from scipy.spatial.distance import cdist
 
 from autooed_b200.solver.base import Solver
-
-
-def lhs(n_var, n_samples):
-    """Random Latin-hypercube design in [0, 1]^n_var (one point per stratum and dimension)."""
-    u = (np.random.rand(n_samples, n_var) + np.arange(n_samples)[:, None]) / n_samples
-    for k in range(n_var):
-        u[:, k] = u[np.random.permutation(n_samples), k]
-    return u
+from autooed_b200.utils.sampling import lhs  # same random-number consumption as the reference's sampler
 
 
 def crowding_distance(F):

@@ -292,6 +292,9 @@ class GaussianProcess(SurrogateModel):
         self.fitted = True
 
     def _refit_single(self, index, X, y):
+        if self.fitted and self._theta is not None and self._Xn is not None and np.array_equal(X, self._Xn) \
+                and np.array_equal(y, self._Yn[:, index]):
+            return  # same data, same deterministic optimiser from the same start: the fit it would redo is the current one
         Yn = np.array(self._Yn if self._Yn is not None and len(self._Yn) == len(y) else np.zeros((len(y), self.n_obj)))
         Yn[:, index] = y
         thetas = np.array(self._theta) if self._theta is not None else np.tile(initial_theta(self.n_var), (self.n_obj, 1))

@@ -117,6 +117,17 @@ int aoed_gp_reset_counters(aoed_gp_t* gp);
  * (n_train <= 232) and the blocked multi-stream path. */
 int aoed_gp_get_fit_counters(aoed_gp_t* gp, int64_t* n_small, int64_t* n_blocked);
 
+/* ---- Thompson-sampling acquisition -----------------------------------------------
+ * replaces ThompsonSampling._evaluate (autooed/mobo/acquisition/ts.py:65-87) incl. its un-normalisation: value, gradient
+ * and Hessian of the random-Fourier-feature posterior sample  f_o(x) = factor_o * sum_j theta_oj cos(W_oj . x + b_oj).
+ *   h_W (n_obj x n_feat x n_var), h_b, h_theta (n_obj x n_feat), h_factor = sqrt(2 sf2 / n_feat), h_y_mean, h_y_scale (n_obj)
+ *   h_Xn (n_rows x n_var) normalised candidates; flags AOED_EVAL_GRAD / AOED_EVAL_HESS
+ * Outputs (may be NULL): F = f * y_scale + y_mean (n_rows x n_obj); dF = df/dx * y_scale (n_rows x n_obj x n_var);
+ * hF = d2f/dx2 in normalised-Y units, as the reference leaves it (n_rows x n_obj x n_var x n_var). */
+int aoed_rff_eval(int device, int64_t n_rows, int n_var, int n_obj, int n_feat, const double* h_W, const double* h_b,
+                  const double* h_theta, const double* h_factor, const double* h_y_mean, const double* h_y_scale,
+                  const double* h_Xn, uint32_t flags, double* h_F, double* h_dF, double* h_hF);
+
 /* ---- multi-objective selection ------------------------------------------------------------------
  * replaces find_pareto_front / check_pareto (autooed/utils/pareto.py:27-62): non-dominated mask of Y (n x m),
  * minimisation; i is kept iff no j has all(Y_j <= Y_i) and any(Y_j < Y_i). */
