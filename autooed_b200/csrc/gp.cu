@@ -351,11 +351,13 @@ void launch_lmlgrad(int nu, int DP, const LmlGradArgs& a, dim3 grid, cudaStream_
 
 template <bool UPPER, int TNV>
 int launch_trmm_cfg(const TrmmArgs& a, int colTiles128, int batch, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
         CU(cudaFuncSetAttribute(trmm_kernel<UPPER, TNV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 int(TrmmCfg<TNV>::SMEM)));
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     TrmmArgs args = a;
     args.colTiles = colTiles128 * (TN / TNV);
@@ -413,20 +415,26 @@ int sm_count(int device) {
     return n[device];
 }
 
+// `ticket`: the launch's tile counter; it must not be shared with a launch that can still be running on ANOTHER stream
+// (launches on one stream are ordered, so a per-stream counter or ring is safe).
 template <bool UPPER>
 int launch_trmm_tma(aoed_gp* gp, const CUtensorMap& mapA, const CUtensorMap& mapB, const TrmmArgs& a, int colTiles,
-                    int batch, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
+                    int batch, cudaStream_t s, int* ticket = nullptr) {
+    static bool attr_set[64] = {false};  // function attributes are per device
+    const int dev = gp->device & 63;
+    if (!attr_set[dev]) {
         CU(cudaFuncSetAttribute(trmm_tma_kernel<UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PT_SMEM)));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     TrmmTmaArgs t;
     t.Out = a.Out; t.strideOut = a.strideOut; t.ldo = a.ldo;
     t.sumsq = a.sumsq; t.strideSS = a.strideSS;
     t.M = a.M; t.Kpad = a.Kpad; t.Npad = gp->Npad; t.mTiles = a.mTiles; t.colTiles = colTiles; t.batch = batch;
-    gp->ticket_slot = (gp->ticket_slot + 1) % 64;
-    t.counter = gp->dTickets + gp->ticket_slot;
+    if (ticket == nullptr) {  // evaluation path: ring on the (single) compute stream
+        gp->ticket_slot = (gp->ticket_slot + 1) % 64;
+        ticket = gp->dTickets + gp->ticket_slot;
+    }
+    t.counter = ticket;
     CU(cudaMemsetAsync(t.counter, 0, sizeof(int), s));
     static const bool debug = getenv("AOED_TRMM_DEBUG") != nullptr;
     if (debug && gp->hDbg == nullptr) {
@@ -791,7 +799,7 @@ int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const doub
         CU(cudaMalloc(&gp->dLinv, size_t(m) * Np * Np * sizeof(double)));
         CU(cudaMalloc(&gp->dLinvT, size_t(m) * Np * Np * sizeof(double)));
         CU(cudaMalloc(&gp->dL, size_t(m) * Np * Np * sizeof(double)));
-        CU(cudaMalloc(&gp->dTickets, 64 * sizeof(int)));
+        CU(cudaMalloc(&gp->dTickets, (64 + kMaxFitCtx) * sizeof(int)));  // ring for the compute stream + one per fit context
         if (gp->trmm_variant == 0) {
             CHK(make_map_2d(&gp->mapLinv, gp->dLinv, int64_t(m) * Np, Np, Np, TM));
             CHK(make_map_2d(&gp->mapLinvT, gp->dLinvT, int64_t(m) * Np, Np, Np, TM));
@@ -1147,7 +1155,7 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
                     t.Out = c.Kinv; t.strideOut = 0; t.ldo = Npad;
                     t.sumsq = nullptr; t.strideSS = 0;
                     t.M = N; t.Kpad = gp->Kpad; t.mTiles = gp->mTiles;
-                    CHK(launch_trmm_tma<true>(gp, c.mapLinvT, c.mapLinv, t, Npad / TN, 1, s));
+                    CHK(launch_trmm_tma<true>(gp, c.mapLinvT, c.mapLinv, t, Npad / TN, 1, s, gp->dTickets + 64 + (b % nctx)));
                     LmlGradArgs ga;
                     ga.Ts = c.Ts; ga.c1c2 = c.c1c2; ga.alpha = c.alpha; ga.Kinv = c.Kinv; ga.partial = c.partial;
                     ga.N = N; ga.Npad = Npad; ga.DP = DP; ga.nBlocksX = nb; ga.nBlocksY = nb;

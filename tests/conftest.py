@@ -15,8 +15,9 @@ def pytest_configure(config):
 
 
 def golden_files():
-    """GP / acquisition fixtures (one per problem shape x nu); pareto_cases.npz is the multi-objective fixture."""
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and "_nu" in f)
+    """GP / acquisition fixtures (one per problem shape x nu); pareto_cases.npz is the multi-objective fixture, ts_*.npz
+    the Thompson-sampling ones."""
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("ts_", "pareto_")))
 
 
 @pytest.fixture(scope="session")
