@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
-    for macro in ("AOED_XCOV_UNROLL", "AOED_XCOV_MINBLOCKS"):  # tuning experiments; defaults live in posterior.cuh
+    for macro in ("AOED_XCOV_UNROLL", "AOED_XCOV_MINBLOCKS", "AOED_XCOV_XS_SMEM"):  # tuning experiments; defaults live in posterior.cuh
         if os.environ.get(macro):
             cmd += [f"-D{macro}={os.environ[macro]}"]
     if verbose:

@@ -44,6 +44,9 @@ struct XcovArgs {
 #ifndef AOED_XCOV_UNROLL
 #define AOED_XCOV_UNROLL 1
 #endif
+#ifndef AOED_XCOV_XS_SMEM
+#define AOED_XCOV_XS_SMEM 0
+#endif
 
 template <int NU, int DP, bool GRAD>
 __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(XcovArgs p) {
@@ -56,9 +59,18 @@ __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(X
     const double* __restrict__ Ts = p.Ts + int64_t(o) * p.Npad * DP;
     const double* __restrict__ alpha = p.alpha + int64_t(o) * p.Npad;
 
-    double xs[DP];
+#if AOED_XCOV_XS_SMEM
+    // candidate coordinates in shared memory ([k][thread]: conflict free) instead of 2*DP registers: more resident warps
+    __shared__ double xsm[DP][XC_THREADS];
 #pragma unroll
-    for (int k = 0; k < DP; ++k) xs[k] = p.XT[int64_t(k) * p.ldc + c] / p.ell[o * DP + k];
+    for (int k = 0; k < DP; ++k) xsm[k][tid] = p.XT[int64_t(k) * p.ldc + c] / p.ell[o * DP + k];
+#define xs(k) xsm[k][tid]
+#else
+    double xsr[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) xsr[k] = p.XT[int64_t(k) * p.ldc + c] / p.ell[o * DP + k];
+#define xs(k) xsr[k]
+#endif
 
     double mu = 0.0, s0 = 0.0;
     double sk[GRAD ? DP : 1];
@@ -83,7 +95,7 @@ __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(X
 #pragma unroll
             for (int k = 0; k < DP; k += 2) {
                 const double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
-                const double d0 = xs[k] - t.x, d1 = xs[k + 1] - t.y;
+                const double d0 = xs(k) - t.x, d1 = xs(k + 1) - t.y;
                 r2 = fma(d0, d0, r2);
                 r2b = fma(d1, d1, r2b);
             }
@@ -120,8 +132,8 @@ __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(X
             for (int k = 0; k < DP; k += 2) {
                 const double2 ta = *reinterpret_cast<const double2*>(&ts[jj][k]);
                 const double2 tb = *reinterpret_cast<const double2*>(&ts[j1][k]);
-                const double a0 = xs[k] - ta.x, a1 = xs[k + 1] - ta.y;
-                const double b0 = xs[k] - tb.x, b1 = xs[k + 1] - tb.y;
+                const double a0 = xs(k) - ta.x, a1 = xs(k + 1) - ta.y;
+                const double b0 = xs(k) - tb.x, b1 = xs(k + 1) - tb.y;
                 ra0 = fma(a0, a0, ra0);
                 ra1 = fma(a1, a1, ra1);
                 rb0 = fma(b0, b0, rb0);
@@ -162,6 +174,7 @@ __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(X
         }
     }
 #endif
+#undef xs
     double* __restrict__ part = p.part + (int64_t(o) * p.JS + js) * (2 + DP) * p.ldc + c;
     part[0] = mu;
     if (GRAD) {

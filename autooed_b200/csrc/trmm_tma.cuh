@@ -58,7 +58,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* db
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (spin > (1u << 21)) {  // ~2 s of 1 us suspends
+        if (spin > (1u << 24)) {  // tens of seconds of 1 us suspends: only a protocol bug gets here
             if (dbg != nullptr && atomicCAS(dbg, 0, where) == 0) {
                 dbg[1] = blockIdx.x; dbg[2] = threadIdx.x; dbg[3] = info; dbg[4] = int(parity);
                 __threadfence_system();
