@@ -29,6 +29,15 @@ WORKLOAD = dict(workload="c4: synthetic GP N=2000 d=20 n_obj=3, Matern-5/2, UCB 
                 l2_policy="inputs larger than L2: every chunk of 16384 candidates streams 3.2 GB of K*, W, V, g/r slabs (126 MB L2), outputs 528 MB per step")
 
 
+WORKLOADS = {
+    "c4": WORKLOAD,
+    # BASELINE.json configs[4]: the sharding sweep shape (8 M candidates over 8 GPUs = 2^20 per GPU, weak scaling)
+    "c5": dict(workload="c5: synthetic GP N=4000 d=32 n_obj=3, Matern-5/2, UCB value+gradient over 2^20 candidates per GPU",
+               n_train=4000, n_var=32, n_obj=3, nu=5, acquisition="ucb", candidates_per_gpu=1 << 20,
+               l2_policy="inputs larger than L2: every chunk of 16384 candidates streams 6.4 GB of K*, W, V, g/r slabs (126 MB L2)"),
+}
+
+
 def make_problem(n_train, d, m, seed=0):
     """Synthetic data of SURVEY.md §8(d): X ~ U[0,1]^{N x d}, Y = sin(XW) + 0.1 X^2 |W|; fixed hyper-parameters."""
     rng = np.random.default_rng(seed)
@@ -536,7 +545,11 @@ def main():
     ap.add_argument("--mode", default="evals", choices=["evals", "fit", "mobo"],
                     help="evals = the contract line (default); fit / mobo = secondary measurements, one JSON line each")
     ap.add_argument("--mobo-iters", type=int, default=20)
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS),
+                    help="c4 = the configuration the metric is quoted on (default); c5 = the N=4000, d=32 sharding-sweep shape")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = WORKLOADS[args.workload]
     if args.mode == "fit":
         return run_fit_mode(args)
     if args.mode == "mobo":
