@@ -1,0 +1,414 @@
+// Blocked version of the one-CTA-per-problem log-marginal-likelihood + gradient kernel (sm_100a, FP64 DMMA).
+//
+// Same contract and shared-memory layout (packed lower triangle) as lml_small_kernel (fit_small.cuh); the three
+// O(N^3) phases are restructured into 16 x 16 blocks whose products run on the FP64 tensor pipe (mma.sync m8n8k4,
+// SASS DMMA) instead of element-wise rank-1 sweeps with a CTA barrier per column:
+//
+//   Cholesky   right-looking blocked: diagonal block factored + inverted by one warp, panel  L21 = A21 L11^-T  and
+//              trailing update  A22 -= L21 L21^T  as block GEMMs spread over all 16 warps
+//   inverse    X = L^-1 in place, block row at a time:  X[k][j] = L11^-1 R[k][j],  R[i][j] -= L[i][k] X[k][j]
+//   K^-1       G = X^T X in place, block row at a time: G[i][j] += X[t][i]^T X[t][j]
+//   gradient   element-wise contraction of (alpha alpha^T - K^-1) with dK/dtheta (no reductions inside the pair loop)
+//
+// Barriers: 3 per block column (13 block columns at N = 200) instead of 3 per column.
+#pragma once
+#include "common.cuh"
+#include "fit.cuh"
+#include "fit_small.cuh"
+
+namespace aoed {
+
+constexpr int FB = 16;       // block size
+constexpr int FBP = FB + 1;  // padded row length of the panel buffer (bank-conflict free fragment loads)
+
+// packed triangle + ONE panel buffer + small vectors; the caller falls back to lml_small_kernel when this exceeds 227 KB
+inline size_t lml_blk_smem(int N, int DP) {
+    const size_t Nr = size_t((N + FB - 1) / FB) * FB;
+    return (size_t(N) * (N + 1) / 2 + 4 * size_t(N) + FBP * Nr + 2 * FB * (FB + 1) + 2 * DP + FS_WARPS * (DP + 2) + 16) *
+           sizeof(double);
+}
+
+// accumulators of one 16 x 16 block: 2 x 2 DMMA tiles; lane (g, q) owns C[8 mi + g][8 ni + 2 q + e]
+struct BlkAcc {
+    double c[2][2][2];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+    }
+};
+
+// acc += A (16 x 16) * B (16 x 16); fa(r, k) and fb(k, n) return operand elements
+template <class FA, class FB_>
+__device__ __forceinline__ void blk_mma(BlkAcc& acc, FA fa, FB_ fb, int g, int q) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int k = 4 * s + q;
+        const double a0 = fa(g, k), a1 = fa(8 + g, k);
+        const double b0 = fb(k, g), b1 = fb(k, 8 + g);
+        dmma884(acc.c[0][0][0], acc.c[0][0][1], a0, b0);
+        dmma884(acc.c[0][1][0], acc.c[0][1][1], a0, b1);
+        dmma884(acc.c[1][0][0], acc.c[1][0][1], a1, b0);
+        dmma884(acc.c[1][1][0], acc.c[1][1][1], a1, b1);
+    }
+}
+
+// visit the 8 elements of the block a lane owns: f(r, c, value&)
+template <class F>
+__device__ __forceinline__ void blk_foreach(BlkAcc& acc, F f, int g, int q) {
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) f(8 * mi + g, 8 * ni + 2 * q + e, acc.c[mi][ni][e]);
+}
+
+template <int NU, int DP>
+__global__ void __launch_bounds__(FS_THREADS, 1) lml_blk_kernel(LmlSmallArgs p) {
+    extern __shared__ __align__(16) double fb_smem[];
+    const int N = p.N, d = p.d;
+    const int nblk = (N + FB - 1) / FB, Nr = nblk * FB;
+    double* Lp = fb_smem;                        // packed lower triangle: (i, j <= i) at tri(i) + j
+    double* yv = Lp + size_t(N) * (N + 1) / 2;   // [N]
+    double* zv = yv + N;                         // [N]
+    double* al = zv + N;                         // [N]
+    double* dg = al + N;                         // [N] diagonal of L (for log|L|)
+    // ONE panel buffer P[Nr][FBP]: rows i below the current block hold the column panel (L[i][k-block][.]), rows j up to
+    // the current block hold the row panel transposed (P[j][r] = X[k-block][r][j]) — the two never overlap
+    double* P = dg + N;
+    double* Dsm = P + size_t(FBP) * Nr;          // [FB][FB+1] diagonal block scratch
+    double* Dinv = Dsm + FB * (FB + 1);          // [FB][FB+1] its inverse
+    double* iell = Dinv + FB * (FB + 1);         // [DP]
+    double* red = iell + 2 * DP + 16;            // [FS_WARPS][DP + 2]
+    __shared__ int s_fail;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int b = blockIdx.x;
+    const double* __restrict__ th = p.theta + int64_t(b) * (d + 2);
+    const double c1 = exp(th[0]), c2 = exp(th[d + 1]);
+    if (tid < DP) iell[tid] = (tid < d) ? exp(-th[1 + tid]) : 0.0;
+    if (tid == 0) s_fail = 0;
+    const double* __restrict__ y = p.Y + int64_t(p.obj[b]) * p.Npad;
+    for (int i = tid; i < N; i += FS_THREADS) yv[i] = y[i];
+    __syncthreads();
+#define FB_STAMP(idx) \
+    if (p.clk != nullptr && tid == 0) p.clk[int64_t(b) * 8 + (idx)] = clock64();
+    FB_STAMP(0)
+
+    // packed-triangle element access with bounds: rows / columns >= N read as 0
+    auto LP = [&](int i, int j) -> double { return (i < N && j <= i) ? Lp[tri(i) + j] : 0.0; };
+
+    // ---- 1: kernel matrix ---------------------------------------------------------------------------------------
+    for (int i = warp; i < N; i += FS_WARPS) {
+        const double* xi = p.X + int64_t(i) * d;
+        for (int j = lane; j <= i; j += 32) {
+            const double* xj = p.X + int64_t(j) * d;
+            double r2 = 0.0;
+            for (int k = 0; k < d; ++k) {
+                const double t = (xi[k] - xj[k]) * iell[k];
+                r2 = fma(t, t, r2);
+            }
+            double phi, gor;
+            kernel_profile<NU>(sqrt(r2), r2, phi, gor);
+            Lp[tri(i) + j] = (i == j) ? (c1 + c2) + kJitter : fma(c1, phi, c2);
+        }
+    }
+    __syncthreads();
+    FB_STAMP(1)
+
+    // ---- 2: blocked Cholesky; the diagonal blocks end up holding L_kk^-1 ------------------------------------------
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k0 = kb * FB;
+        if (warp == 0) {
+            // diagonal block -> Dsm (lower; identity padding beyond N), unblocked Cholesky, then its inverse -> Dinv
+            for (int e = lane; e < FB * FB; e += 32) {
+                const int r = e / FB, c = e % FB;
+                double v = 0.0;
+                if (c <= r) v = (k0 + r < N) ? Lp[tri(k0 + r) + k0 + c] : (r == c ? 1.0 : 0.0);
+                Dsm[r * (FB + 1) + c] = v;
+            }
+            __syncwarp();
+            bool bad = false;
+            for (int c = 0; c < FB; ++c) {
+                const double dcc = Dsm[c * (FB + 1) + c];
+                if (!(dcc > 0.0)) {
+                    bad = true;
+                    break;
+                }
+                const double ip = rsqrt(dcc);
+                __syncwarp();
+                const int r = lane & 15, h = lane >> 4;
+                if (h == 0 && r > c) Dsm[r * (FB + 1) + c] *= ip;
+                if (lane == 0) {
+                    Dsm[c * (FB + 1) + c] = dcc * ip;
+                    Dinv[c * (FB + 1) + c] = ip;  // 1 / L_cc
+                }
+                __syncwarp();
+                if (r > c) {
+                    // all loads first (independent), then the multiply-adds and stores: the chain per pivot is what bounds
+                    // this warp, and the compiler cannot reorder shared-memory reads across the writes by itself
+                    const double lrc = Dsm[r * (FB + 1) + c];
+                    double lc[FB / 2], av[FB / 2];
+#pragma unroll
+                    for (int t = 0; t < FB / 2; ++t) {
+                        const int cc = c + 1 + h + 2 * t;
+                        const bool on = cc <= r;
+                        lc[t] = on ? Dsm[cc * (FB + 1) + c] : 0.0;
+                        av[t] = on ? Dsm[r * (FB + 1) + cc] : 0.0;
+                    }
+#pragma unroll
+                    for (int t = 0; t < FB / 2; ++t) {
+                        const int cc = c + 1 + h + 2 * t;
+                        if (cc <= r) Dsm[r * (FB + 1) + cc] = fma(-lrc, lc[t], av[t]);
+                    }
+                }
+                __syncwarp();
+            }
+            if (bad) {
+                if (lane == 0) s_fail = 1;
+            } else {
+                if (lane < FB && k0 + lane < N) dg[k0 + lane] = Dsm[lane * (FB + 1) + lane];
+                // inverse of the lower-triangular block, one column per lane (forward substitution in registers)
+                if (lane < FB) {
+                    const int j = lane;
+                    double x[FB];
+#pragma unroll
+                    for (int i = 0; i < FB; ++i) x[i] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < FB; ++i) {
+                        if (i < j) continue;
+                        const double idiag = Dinv[i * (FB + 1) + i];
+                        if (i == j) {
+                            x[i] = idiag;
+                        } else {
+                            double s = 0.0;
+#pragma unroll
+                            for (int k = 0; k < FB; ++k)
+                                if (k >= j && k < i) s = fma(Dsm[i * (FB + 1) + k], x[k], s);
+                            x[i] = -s * idiag;
+                        }
+                    }
+                    __syncwarp(0xffff);
+#pragma unroll
+                    for (int i = 0; i < FB; ++i) Dinv[i * (FB + 1) + j] = x[i];  // upper part = 0
+                }
+                __syncwarp();
+                // the diagonal block of the packed matrix now stores L_kk^-1 (phase 3 needs only that)
+                for (int e = lane; e < FB * FB; e += 32) {
+                    const int r = e / FB, c = e % FB;
+                    if (c <= r && k0 + r < N) Lp[tri(k0 + r) + k0 + c] = Dinv[r * (FB + 1) + c];
+                }
+            }
+        }
+        __syncthreads();
+        if (s_fail) break;
+        // panel: L[ib][kb] = A[ib][kb] * Dinv^T for the row blocks below, one block per warp; copy into colP as well
+        for (int ib = kb + 1 + warp; ib < nblk; ib += FS_WARPS) {
+            const int i0 = ib * FB;
+            BlkAcc acc;
+            acc.zero();
+            blk_mma(acc, [&](int r, int k) { return LP(i0 + r, k0 + k); },
+                    [&](int k, int n) { return Dinv[n * (FB + 1) + k]; }, g, q);
+            __syncwarp();
+            blk_foreach(acc, [&](int r, int c, double& v) {
+                if (i0 + r < N && k0 + c < N) Lp[tri(i0 + r) + k0 + c] = v;
+                P[(i0 + r) * FBP + c] = (i0 + r < N && k0 + c < N) ? v : 0.0;
+            }, g, q);
+        }
+        __syncthreads();
+        // trailing update: A[ib][jb] -= L[ib][kb] L[jb][kb]^T for kb < jb <= ib
+        {
+            const int nt = nblk - kb - 1;
+            const int npair = nt * (nt + 1) / 2;
+            for (int pr = warp; pr < npair; pr += FS_WARPS) {
+                int bi = int((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
+                while (bi * (bi + 1) / 2 > pr) --bi;
+                while ((bi + 1) * (bi + 2) / 2 <= pr) ++bi;
+                const int bj = pr - bi * (bi + 1) / 2;
+                const int i0 = (kb + 1 + bi) * FB, j0 = (kb + 1 + bj) * FB;
+                BlkAcc acc;
+                acc.zero();
+                blk_mma(acc, [&](int r, int k) { return P[(i0 + r) * FBP + k]; },
+                        [&](int k, int n) { return P[(j0 + n) * FBP + k]; }, g, q);
+                blk_foreach(acc, [&](int r, int c, double& v) {
+                    const int i = i0 + r, j = j0 + c;
+                    if (i < N && j <= i) Lp[tri(i) + j] -= v;
+                }, g, q);
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    double* out = p.res + int64_t(b) * (d + 3);
+    double logdet = 0.0;
+    if (warp == 0 && !s_fail) {
+        for (int k = lane; k < N; k += 32) logdet += log(dg[k]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) logdet += __shfl_xor_sync(0xffffffffu, logdet, off);
+    }
+    if (s_fail) {
+        if (tid == 0) out[0] = -INFINITY;
+        if (tid < d + 2) out[1 + tid] = 0.0;
+        return;
+    }
+    FB_STAMP(2)
+
+    // ---- 3: X = L^-1 in place (block rows top to bottom) -------------------------------------------------------------
+    // invariant before step kb: block rows < kb hold X; rows >= kb hold R = I - (partial products) in columns < kb,
+    // L in columns >= kb (strictly lower blocks) and L_kk^-1 on the diagonal
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k0 = kb * FB;
+        // (a) row block kb: X[kb][jb] = Dinv_kb * R[kb][jb] (jb < kb); X[kb][kb] = Dinv_kb.  Result -> rowP (and storage)
+        for (int jb = warp; jb <= kb; jb += FS_WARPS) {
+            const int j0 = jb * FB;
+            BlkAcc acc;
+            acc.zero();
+            if (jb < kb) {
+                blk_mma(acc, [&](int r, int k) { return (k <= r) ? LP(k0 + r, k0 + k) : 0.0; },
+                        [&](int k, int n) { return LP(k0 + k, j0 + n); }, g, q);
+            } else {
+                blk_foreach(acc, [&](int r, int c, double& v) { v = (c <= r) ? LP(k0 + r, k0 + c) : 0.0; }, g, q);
+            }
+            __syncwarp();
+            blk_foreach(acc, [&](int r, int c, double& v) {
+                if (jb < kb && k0 + r < N) Lp[tri(k0 + r) + j0 + c] = v;
+                P[(j0 + c) * FBP + r] = (k0 + r < N) ? v : 0.0;
+            }, g, q);
+        }
+        // (b) column panel L[ib][kb] for ib > kb -> colP
+        for (int e = tid; e < (Nr - k0 - FB) * FB; e += FS_THREADS) {
+            const int i = k0 + FB + e / FB, c = e % FB;
+            P[i * FBP + c] = LP(i, k0 + c);
+        }
+        __syncthreads();
+        // (c) R[ib][jb] = (jb == kb ? 0 : R[ib][jb]) - L[ib][kb] * X[kb][jb]   for ib > kb, jb <= kb
+        {
+            const int nrow = nblk - kb - 1, ncol = kb + 1;
+            for (int pr = warp; pr < nrow * ncol; pr += FS_WARPS) {
+                const int ib = kb + 1 + pr / ncol, jb = pr % ncol;
+                const int i0 = ib * FB, j0 = jb * FB;
+                BlkAcc acc;
+                acc.zero();
+                blk_mma(acc, [&](int r, int k) { return P[(i0 + r) * FBP + k]; },
+                        [&](int k, int n) { return P[(j0 + n) * FBP + k]; }, g, q);
+                blk_foreach(acc, [&](int r, int c, double& v) {
+                    const int i = i0 + r, j = j0 + c;
+                    if (i < N && j < N) Lp[tri(i) + j] = (jb == kb ? 0.0 : Lp[tri(i) + j]) - v;
+                }, g, q);
+            }
+        }
+        __syncthreads();
+    }
+    FB_STAMP(3)
+
+    // ---- 4: z = X y, alpha = X^T z ------------------------------------------------------------------------------------
+    for (int i = warp; i < N; i += FS_WARPS) {
+        const double* row = Lp + tri(i);
+        double s = 0.0;
+        for (int k = lane; k <= i; k += 32) s = fma(row[k], yv[k], s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) zv[i] = s;
+    }
+    __syncthreads();
+    for (int j = warp; j < N; j += FS_WARPS) {
+        double s = 0.0;
+        for (int i = j + lane; i < N; i += 32) s = fma(Lp[tri(i) + j], zv[i], s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) al[j] = s;
+    }
+    if (warp == 0) {
+        double qq = 0.0;
+        for (int i = lane; i < N; i += 32) qq = fma(zv[i], zv[i], qq);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, off);
+        if (lane == 0) out[0] = -0.5 * qq - logdet - 0.5 * N * 1.8378770664093453;
+    }
+    __syncthreads();
+    FB_STAMP(4)
+    if (!p.want_grad) return;
+
+    // ---- 5a: G = X^T X in place (block rows top to bottom) ---------------------------------------------------------------
+    for (int tb = 0; tb < nblk; ++tb) {
+        const int t0 = tb * FB;
+        // row panel X[tb][0 .. tb] -> rowP (the diagonal block is lower triangular)
+        for (int e = tid; e < FB * (t0 + FB); e += FS_THREADS) {
+            const int r = e / (t0 + FB), j = e % (t0 + FB);
+            P[j * FBP + r] = LP(t0 + r, j);
+        }
+        __syncthreads();
+        {
+            const int nb = tb + 1, npair = nb * (nb + 1) / 2;
+            for (int pr = warp; pr < npair; pr += FS_WARPS) {
+                int ib = int((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
+                while (ib * (ib + 1) / 2 > pr) --ib;
+                while ((ib + 1) * (ib + 2) / 2 <= pr) ++ib;
+                const int jb = pr - ib * (ib + 1) / 2;
+                const int i0 = ib * FB, j0 = jb * FB;
+                BlkAcc acc;
+                acc.zero();
+                blk_mma(acc, [&](int r, int k) { return P[(i0 + r) * FBP + k]; },
+                        [&](int k, int n) { return P[(j0 + n) * FBP + k]; }, g, q);
+                blk_foreach(acc, [&](int r, int c, double& v) {
+                    const int i = i0 + r, j = j0 + c;
+                    if (i < N && j <= i) Lp[tri(i) + j] = (ib == tb ? 0.0 : Lp[tri(i) + j]) + v;
+                }, g, q);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- 5b: gradient contraction ---------------------------------------------------------------------------------------
+    double gacc[DP + 2];
+#pragma unroll
+    for (int k = 0; k < DP + 2; ++k) gacc[k] = 0.0;
+    for (int i = warp; i < N; i += FS_WARPS) {
+        const double* xi = p.X + int64_t(i) * d;
+        const double ai = al[i];
+        for (int j = lane; j <= i; j += 32) {
+            double w = ai * al[j] - Lp[tri(i) + j];
+            if (i != j) w *= 2.0;
+            const double* xj = p.X + int64_t(j) * d;
+            double r2 = 0.0;
+            for (int k = 0; k < d; ++k) {
+                const double t = (xi[k] - xj[k]) * iell[k];
+                r2 = fma(t, t, r2);
+            }
+            const double r = sqrt(r2);
+            double phi, gor;
+            kernel_profile<NU>(r, r2, phi, gor);
+            if (i == j) phi = 1.0;
+            gacc[0] = fma(w * c1, phi, gacc[0]);
+            const double wh = w * c1 * h_profile<NU>(r, r2, phi);
+#pragma unroll
+            for (int k = 0; k < DP; ++k) {
+                const double t = (k < d) ? (xi[k] - xj[k]) * iell[k] : 0.0;
+                gacc[1 + k] = fma(wh, t * t, gacc[1 + k]);
+            }
+            gacc[DP + 1] = fma(w, c2, gacc[DP + 1]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < DP + 2; ++k) {
+        double v = gacc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp * (DP + 2) + k] = v;
+    }
+    __syncthreads();
+    if (tid < DP + 2) {
+        double s = 0.0;
+        for (int w8 = 0; w8 < FS_WARPS; ++w8) s += red[w8 * (DP + 2) + tid];
+        s *= 0.5;
+        if (tid == 0) out[1] = s;
+        else if (tid == DP + 1) out[1 + d + 1] = s;
+        else if (tid - 1 < d) out[1 + tid] = s;
+    }
+    FB_STAMP(5)
+#undef FB_STAMP
+}
+
+}  // namespace aoed

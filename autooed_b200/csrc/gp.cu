@@ -15,6 +15,7 @@
 #include "../../include/aoed_b200.h"
 #include "fit.cuh"
 #include "fit_small.cuh"
+#include "fit_small2.cuh"
 #include "hessian.cuh"
 #include "posterior.cuh"
 #include "trmm.cuh"
@@ -980,6 +981,37 @@ int launch_lml_small_dp(int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t 
     return AOED_OK;
 }
 
+template <int NU>
+int launch_lml_blk_dp(int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t s) {
+    const size_t sm = lml_blk_smem(a.N, DP);
+#define FBK_CASE(D)                                                                                            \
+    case D:                                                                                                    \
+        CU(cudaFuncSetAttribute(lml_blk_kernel<NU, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm))); \
+        lml_blk_kernel<NU, D><<<n_prob, FS_THREADS, sm, s>>>(a);                                               \
+        break;
+    switch (DP) {
+        FBK_CASE(8)
+        FBK_CASE(16)
+        FBK_CASE(24)
+        default:
+            CU(cudaFuncSetAttribute(lml_blk_kernel<NU, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
+            lml_blk_kernel<NU, 32><<<n_prob, FS_THREADS, sm, s>>>(a);
+            break;
+    }
+#undef FBK_CASE
+    CU(cudaGetLastError());
+    return AOED_OK;
+}
+
+int launch_lml_blk(int nu, int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t s) {
+    switch (nu) {
+        case 1: return launch_lml_blk_dp<1>(DP, a, n_prob, s);
+        case 3: return launch_lml_blk_dp<3>(DP, a, n_prob, s);
+        case 5: return launch_lml_blk_dp<5>(DP, a, n_prob, s);
+        default: return launch_lml_blk_dp<-1>(DP, a, n_prob, s);
+    }
+}
+
 int launch_lml_small(int nu, int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t s) {
     switch (nu) {
         case 1: return launch_lml_small_dp<1>(DP, a, n_prob, s);
@@ -1101,12 +1133,16 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
             CU(cudaMalloc(&dclk, size_t(n_prob) * 8 * sizeof(long long)));
             a.clk = dclk;
         }
-        CHK(launch_lml_small(gp->nu, DP, a, n_prob, s0));
+        // blocked DMMA kernel when its panel buffer fits beside the packed triangle (N <= ~208), else the rank-1 kernel
+        static const bool force_v1 = getenv("AOED_FIT_SMALL") && strcmp(getenv("AOED_FIT_SMALL"), "v1") == 0;
+        const bool blocked = !force_v1 && lml_blk_smem(N, DP) <= 227 * 1024;
+        if (blocked) CHK(launch_lml_blk(gp->nu, DP, a, n_prob, s0));
+        else CHK(launch_lml_small(gp->nu, DP, a, n_prob, s0));
         if (stamp) {
             long long h[8];
             CU(cudaMemcpyAsync(h, dclk, sizeof(h), cudaMemcpyDeviceToHost, s0));
             CU(cudaStreamSynchronize(s0));
-            fprintf(stderr, "lml_small N=%d cycles: kmat %lld chol %lld inv %lld alpha %lld grad %lld\n", N, h[1] - h[0],
+            fprintf(stderr, "lml_small%s N=%d cycles: kmat %lld chol %lld inv %lld alpha %lld grad %lld\n", blocked ? "(blocked)" : "", N, h[1] - h[0],
                     h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
             cudaFree(dclk);
         }

@@ -30,12 +30,7 @@ def grad_tol(nu):
     return 1e-6 if nu in (5, -1) else 1e-8
 
 
-@pytest.mark.parametrize("path", ["small", "blocked"])
-@pytest.mark.parametrize("name", FILES)
-def test_lml_batch_vs_reference(name, path, monkeypatch):
-    """All (objective x probe theta) problems of a fixture in ONE batched call."""
-    if path == "blocked":
-        monkeypatch.setenv("AOED_FIT_PATH", "blocked")
+def check_lml_batch(name, counter):
     g = load(name)
     nu = int(g["nu"])
     gp = model_for(g)
@@ -51,8 +46,29 @@ def test_lml_batch_vs_reference(name, path, monkeypatch):
     # value-only call gives the same values
     lml2, none = gp.log_marginal_likelihood_batch(obj, thetas, False)
     assert none is None and np.array_equal(lml, lml2)
-    info = gp.fit_counters()
-    assert info["small" if path == "small" else "blocked"] == 2 * m * 3
+    assert gp.fit_counters()[counter] == 2 * m * 3
+
+
+@pytest.mark.parametrize("path", ["small", "blocked"])
+@pytest.mark.parametrize("name", FILES)
+def test_lml_batch_vs_reference(name, path, monkeypatch):
+    """All (objective x probe theta) problems of a fixture in ONE batched call, on the one-CTA-per-problem kernel
+    (blocked DMMA version) and on the multi-stream path for large N."""
+    if path == "blocked":
+        monkeypatch.setenv("AOED_FIT_PATH", "blocked")
+    check_lml_batch(name, "blocked" if path == "blocked" else "small")
+
+
+def test_lml_batch_rank1_kernel_vs_reference():
+    """The rank-1 predecessor of the one-CTA kernel still serves 208 < N <= 232; the choice is latched per process, so
+    the fixtures are replayed in a child process with AOED_FIT_SMALL=v1."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import os, sys; os.environ['AOED_FIT_SMALL'] = 'v1'; sys.path[:0] = [%r, %r]; import test_gpu_fit as t; "
+            "[t.check_lml_batch(n, 'small') for n in t.FILES]; print('ok')" % (here, os.path.dirname(here)))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stderr[-2000:]
 
 
 @pytest.mark.parametrize("nu", [1, 3, 5, -1])
