@@ -212,15 +212,25 @@ __global__ void __launch_bounds__(XC_THREADS) gradsum_kernel(GradsumArgs p) {
         __syncthreads();
         for (int i = tid; i < nj * DP; i += XC_THREADS) (&ts[0][0])[i] = Ts[int64_t(j0) * DP + i];
         __syncthreads();
-#pragma unroll 4
-        for (int jj = 0; jj < nj; ++jj) {
-            const double wv = Gr[int64_t(j0 + jj) * p.ldc] * V[int64_t(j0 + jj) * p.ldc];
-            s0 += wv;
+        // the kernel is HBM bound (two 8-byte streams per training point): issue the loads of 8 points before using them
+        for (int jb = 0; jb < nj; jb += 8) {
+            double wv[8];
 #pragma unroll
-            for (int k = 0; k < DP; k += 2) {
-                double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
-                sk[k] = fma(wv, t.x, sk[k]);
-                sk[k + 1] = fma(wv, t.y, sk[k + 1]);
+            for (int u = 0; u < 8; ++u) {
+                const int jj = min(jb + u, nj - 1);
+                const double pr = Gr[int64_t(j0 + jj) * p.ldc] * V[int64_t(j0 + jj) * p.ldc];
+                wv[u] = (jb + u < nj) ? pr : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int jj = min(jb + u, nj - 1);
+                s0 += wv[u];
+#pragma unroll
+                for (int k = 0; k < DP; k += 2) {
+                    double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
+                    sk[k] = fma(wv[u], t.x, sk[k]);
+                    sk[k + 1] = fma(wv[u], t.y, sk[k + 1]);
+                }
             }
         }
     }
