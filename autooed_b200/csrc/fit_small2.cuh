@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_blk_kernel(LmlSmallArgs p) 
     for (int kb = 0; kb < nblk; ++kb) {
         const int k0 = kb * FB;
         if (warp == 0) {
+            const long long tdiag0 = (p.clk != nullptr) ? clock64() : 0;
             // diagonal block -> Dsm (lower; identity padding beyond N), unblocked Cholesky, then its inverse -> Dinv
             for (int e = lane; e < FB * FB; e += 32) {
                 const int r = e / FB, c = e % FB;
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_blk_kernel(LmlSmallArgs p) 
                 }
                 __syncwarp();
             }
+            const long long tdiag1 = (p.clk != nullptr) ? clock64() : 0;
+            if (p.clk != nullptr && lane == 0) p.clk[int64_t(b) * 8 + 6] = (kb == 0 ? 0 : p.clk[int64_t(b) * 8 + 6]) + (tdiag1 - tdiag0);
             if (bad) {
                 if (lane == 0) s_fail = 1;
             } else {
@@ -201,6 +204,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_blk_kernel(LmlSmallArgs p) 
                     if (c <= r && k0 + r < N) Lp[tri(k0 + r) + k0 + c] = Dinv[r * (FB + 1) + c];
                 }
             }
+            if (p.clk != nullptr && lane == 0)
+                p.clk[int64_t(b) * 8 + 7] = (kb == 0 ? 0 : p.clk[int64_t(b) * 8 + 7]) + (clock64() - tdiag1);
         }
         __syncthreads();
         if (s_fail) break;

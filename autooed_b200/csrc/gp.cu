@@ -1142,8 +1142,10 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
             long long h[8];
             CU(cudaMemcpyAsync(h, dclk, sizeof(h), cudaMemcpyDeviceToHost, s0));
             CU(cudaStreamSynchronize(s0));
-            fprintf(stderr, "lml_small%s N=%d cycles: kmat %lld chol %lld inv %lld alpha %lld grad %lld\n", blocked ? "(blocked)" : "", N, h[1] - h[0],
-                    h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
+            fprintf(stderr, "lml_small%s N=%d cycles: kmat %lld chol %lld inv %lld alpha %lld grad %lld", blocked ? "(blocked)" : "", N,
+                    h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
+            if (blocked) fprintf(stderr, " | diagonal blocks: factor %lld invert+store %lld", h[6], h[7]);
+            fprintf(stderr, "\n");
             cudaFree(dclk);
         }
         gp->n_launches++;
