@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libaoed_b200.so")
-SOURCES = ["gp.cu", "moo.cu", "rff.cu"]
+SOURCES = ["gp.cu", "moo.cu", "rff.cu", "nsga2.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "aoed_b200.h")]
 
 

@@ -148,15 +148,53 @@ class NSGA2Algorithm:
         return X, F
 
 
+def device_nsga2(acquisition, X0, xl, xu, pop_size, n_gen, seed):
+    """The whole generation loop on the GPU (`aoed_nsga2_run`): no host round trip per generation."""
+    import ctypes
+
+    from autooed_b200 import _lib
+    sm = acquisition.surrogate_model
+    lib, h = _lib.load(), sm._ensure_handle()
+    X0 = _lib.as_f64(X0)
+    d, m = X0.shape[1], sm.n_obj
+    param = acquisition._param()
+    param = None if param is None else _lib.as_f64(param)
+    Xo, Fo = np.empty((pop_size, d)), np.empty((pop_size, m))
+    n_out, n_eval = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(lib.aoed_nsga2_run(h, sm.device, d, m, acquisition.kind, _lib.ptr(param), X0.shape[0], _lib.ptr(X0),
+                                  _lib.ptr(_lib.as_f64(xl)), _lib.ptr(_lib.as_f64(xu)), pop_size, n_gen, seed, _lib.ptr(Xo),
+                                  _lib.ptr(Fo), ctypes.byref(n_out), ctypes.byref(n_eval)))
+    return Xo[:n_out.value], Fo[:n_out.value], n_eval.value
+
+
 class NSGA2(Solver):
     '''
     Solver based on NSGA-II.
     '''
-    def __init__(self, problem, n_gen=200, pop_size=200, rank_fn=None, **kwargs):
+    def __init__(self, problem, n_gen=200, pop_size=200, rank_fn=None, on_device=True, **kwargs):
         super().__init__(problem)
         self.n_gen = n_gen
+        self.on_device = on_device
         self.algo = NSGA2Algorithm(pop_size=pop_size, rank_fn=rank_fn)
+        self.n_eval = 0
+
+    def _device_eligible(self, n_init):
+        """The device loop covers the fused GP acquisitions on unconstrained problems that fit its one-CTA sort."""
+        from autooed_b200 import _lib
+        acq = self.problem.acquisition
+        sm = getattr(acq, 'surrogate_model', None)
+        return (self.on_device and getattr(self.real_problem, 'n_constr', 0) == 0
+                and getattr(acq, 'kind', _lib.ACQ_NONE) != _lib.ACQ_NONE and not getattr(acq, 'exact', False)
+                and hasattr(sm, '_ensure_handle') and sm.n_var <= 32 and sm.n_obj <= 8
+                and max(n_init, self.algo.pop_size) + self.algo.pop_size <= 4096)
 
     def _solve(self, X, Y, batch_size):
         X = np.vstack([X, lhs(X.shape[1], batch_size)])  # nsga2.py:25 (the reference samples the unit cube as well)
-        return self.algo.minimize(self.problem, X, self.n_gen)
+        if self._device_eligible(len(X)):
+            seed = int(np.random.randint(0, 2 ** 31 - 1))  # the run follows the global numpy seed like the host path
+            Xc, Fc, self.n_eval = device_nsga2(self.problem.acquisition, X, self.problem.xl, self.problem.xu,
+                                               self.algo.pop_size, self.n_gen, seed)
+            return Xc, Fc
+        out = self.algo.minimize(self.problem, X, self.n_gen)
+        self.n_eval = self.algo.n_eval
+        return out

@@ -497,7 +497,7 @@ def run_mobo_mode(args):
                 opt = MOBO(prob, sur, acq, NSGA2(prob, n_gen=c["gens"], pop_size=c["pop"], rank_fn=mo.pareto_rank), _OracleHVI())
                 n_it = c["cpu_iters"]
             # where the iteration goes: surrogate fit, acquisition calls + non-dominated sorting inside the solver, selection
-            split = {"fit": 0.0, "acq_evaluate": 0.0, "rank": 0.0, "select": 0.0}
+            split = {"fit": 0.0, "solve": 0.0, "acq_evaluate": 0.0, "rank": 0.0, "select": 0.0}
 
             def timed(obj, name, key):
                 fn = getattr(obj, name)
@@ -511,6 +511,7 @@ def run_mobo_mode(args):
                 setattr(obj, name, wrapper)
 
             timed(sur, "fit", "fit")
+            timed(opt.solver, "solve", "solve")  # contains acq_evaluate and rank when the generation loop runs on the host
             timed(acq, "evaluate", "acq_evaluate")
             timed(opt.solver.algo, "rank_fn", "rank")
             timed(opt.selection, "select", "select")
@@ -528,6 +529,7 @@ def run_mobo_mode(args):
             hv = mo.hypervolume(Y, ref) if arm == "cpu_port" else calc_hypervolume(Y, ref)
             print(json.dumps({"mode": "mobo", "config": c["name"], "arm": arm, "acquisition": c["acq"], "pop": c["pop"],
                               "generations": c["gens"], "batch": c["batch"], "iterations": n_it, "n_final": len(X),
+                              "solver": "device-resident NSGA-II" if (arm == "b200" and opt.solver._device_eligible(len(X))) else "host NSGA-II",
                               "s_per_iteration": float(np.mean(times)), "s_first": times[0], "s_last": times[-1],
                               "s_per_iteration_split": {k: v / n_it for k, v in split.items()},
                               "hypervolume_of_evaluated_set": hv, "cpu_threads": threads if arm == "cpu_port" else None}),

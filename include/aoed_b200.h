@@ -117,6 +117,19 @@ int aoed_gp_reset_counters(aoed_gp_t* gp);
  * (n_train <= 232) and the blocked multi-stream path. */
 int aoed_gp_get_fit_counters(aoed_gp_t* gp, int64_t* n_small, int64_t* n_blocked);
 
+/* ---- NSGA-II on the device -----------------------------------------------------------
+ * replaces the pymoo NSGA2 + minimize(('n_gen', G)) loop of autooed/mobo/solver/nsga2.py:17-30 for unconstrained problems:
+ * the generation loop (variation, duplicate elimination, acquisition evaluation through the fitted model `gp`,
+ * non-dominated sorting, crowding, survival) runs on the GPU without host synchronisation.
+ *   acq_kind / h_acq_param as for aoed_gp_eval (IDENTITY .. PI); h_X0 (n_init x n_var): initial sampling in CONTINUOUS
+ *   space, taken as is (generation 1 = its evaluation); h_xl, h_xu (n_var): bounds; pymoo 0.4.1 operator defaults.
+ * Outputs: h_X (pop_size x n_var), h_F (pop_size x n_obj) — the final population and its acquisition values (only the first
+ * *h_n_out rows are valid: min(n_init, pop_size) when n_gen == 1, else pop_size); *h_n_eval = acquisition evaluations
+ * that were not discarded as duplicates.  n_init + pop_size <= 4096. */
+int aoed_nsga2_run(aoed_gp_t* gp, int device, int n_var, int n_obj, int acq_kind, const double* h_acq_param, int64_t n_init,
+                   const double* h_X0, const double* h_xl, const double* h_xu, int pop_size, int n_gen, uint64_t seed,
+                   double* h_X, double* h_F, int64_t* h_n_out, int64_t* h_n_eval);
+
 /* ---- Thompson-sampling acquisition -----------------------------------------------
  * replaces ThompsonSampling._evaluate (autooed/mobo/acquisition/ts.py:65-87) incl. its un-normalisation: value, gradient
  * and Hessian of the random-Fourier-feature posterior sample  f_o(x) = factor_o * sum_j theta_oj cos(W_oj . x + b_oj).
