@@ -55,6 +55,13 @@ class ThompsonSampling(Acquisition):
             self.bs.append(b)
             self.sf2s.append(sf2)
 
+    def device_sample(self):
+        """The fitted sample as the contiguous arrays the C ABI takes: (W, b, theta, factor, y_mean, y_scale)."""
+        m, M = len(self.thetas), self.M
+        ys = self.normalization.y_scaler
+        return (_lib.as_f64(np.stack(self.Ws)), _lib.as_f64(np.stack(self.bs).reshape(m, M)), _lib.as_f64(np.stack(self.thetas)),
+                _lib.as_f64(np.sqrt(2. * np.asarray(self.sf2s) / M)), _lib.as_f64(ys.mean_), _lib.as_f64(ys.scale_))
+
     def _evaluate(self, X, gradient, hessian, dtype='continuous'):
         if dtype != 'normalized':
             X = self.normalization.do(x=X)
@@ -64,16 +71,13 @@ class ThompsonSampling(Acquisition):
         lib = _lib.load()
         _lib.require_device()
         C, d, m, M = X.shape[0], X.shape[1], len(self.thetas), self.M
-        ys = self.normalization.y_scaler
-        W, b = _lib.as_f64(np.stack(self.Ws)), _lib.as_f64(np.stack(self.bs).reshape(m, M))
-        theta = _lib.as_f64(np.stack(self.thetas))
-        factor = _lib.as_f64(np.sqrt(2. * np.asarray(self.sf2s) / M))
+        W, b, theta, factor, y_mean, y_scale = self.device_sample()
         F = _lib.empty((C, m))
         dF = _lib.empty((C, m, d)) if gradient else None
         hF = _lib.empty((C, m, d, d)) if hessian else None
         flags = (_lib.EVAL_GRAD if gradient else 0) | (_lib.EVAL_HESS if hessian else 0)
         device = getattr(self.surrogate_model, 'device', 0)
         _lib.check(lib.aoed_rff_eval(device, C, d, m, M, _lib.ptr(W), _lib.ptr(b), _lib.ptr(theta), _lib.ptr(factor),
-                                     _lib.ptr(_lib.as_f64(ys.mean_)), _lib.ptr(_lib.as_f64(ys.scale_)), _lib.ptr(X), flags,
+                                     _lib.ptr(y_mean), _lib.ptr(y_scale), _lib.ptr(X), flags,
                                      _lib.ptr(F), _lib.ptr(dF), _lib.ptr(hF)))
         return F, dF, hF

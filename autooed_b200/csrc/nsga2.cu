@@ -22,6 +22,9 @@
 #include "../../include/aoed_b200.h"
 #include "common.cuh"
 #include "rank.cuh"
+#include "rff.cuh"
+
+#include <functional>
 
 extern "C" int aoed_detail_fail(int code, const char* msg);
 
@@ -300,13 +303,17 @@ int launch_rank(int m, const double* YT, int n, int32_t* rank, cudaStream_t s) {
 
 }  // namespace
 
-extern "C" int aoed_nsga2_run(aoed_gp_t* gp, int device, int n_var, int n_obj, int acq_kind, const double* h_acq_param,
-                              int64_t n_init, const double* h_X0, const double* h_xl, const double* h_xu, int pop_size,
-                              int n_gen, uint64_t seed, double* h_X, double* h_F, int64_t* h_n_out, int64_t* h_n_eval) {
-    if (!gp || !h_X0 || !h_xl || !h_xu || !h_X || !h_F || !h_n_out) return nfail(AOED_ERR_INVALID, "null argument");
+namespace {
+
+// evaluator: (stream, normalised candidates [rows][d] on the device, rows, output [rows][m] on the device) -> rc
+using Evaluator = std::function<int(cudaStream_t, const double*, int64_t, double*)>;
+
+int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64_t n_init, const double* h_X0, const double* h_xl,
+               const double* h_xu, int pop_size, int n_gen, uint64_t seed, double* h_X, double* h_F, int64_t* h_n_out,
+               int64_t* h_n_eval) {
+    if (!h_X0 || !h_xl || !h_xu || !h_X || !h_F || !h_n_out) return nfail(AOED_ERR_INVALID, "null argument");
     if (n_init < 1 || pop_size < 2 || n_gen < 1) return nfail(AOED_ERR_INVALID, "n_init >= 1, pop_size >= 2, n_gen >= 1 required");
     if (n_var < 1 || n_var > NS_MAX_D) return nfail(AOED_ERR_UNSUPPORTED, "n_var > 32 is not supported yet");
-    if (acq_kind < AOED_ACQ_IDENTITY || acq_kind > AOED_ACQ_PI) return nfail(AOED_ERR_INVALID, "an acquisition kind is required");
     const int d = n_var, m = n_obj, P = pop_size;
     const int64_t cap = std::max<int64_t>(n_init, P);  // the initial sampling is taken as is, even when larger than pop_size
     if (cap + P > RS_MAX_N || rank_small_smem(m, int(cap + P)) > 200 * 1024)
@@ -319,7 +326,6 @@ extern "C" int aoed_nsga2_run(aoed_gp_t* gp, int device, int n_var, int n_obj, i
         cudaStream_t s;
         ~StreamGuard() { cudaStreamDestroy(s); }
     } sguard{s};
-    const uint32_t flags = acq_kind >= AOED_ACQ_UCB ? AOED_EVAL_STD : 0u;
     NBuf bX[2], bF[2], bR[2], bC[2], bXoff, bXn, bFoff, bDup, bYT, bRank, bCrowd, bSel, bXl, bXu, bEval;
     for (int i = 0; i < 2; ++i) {
         NCU(cudaMalloc(&bX[i].p, size_t(cap) * d * sizeof(double)));
@@ -345,8 +351,7 @@ extern "C" int aoed_nsga2_run(aoed_gp_t* gp, int device, int n_var, int n_obj, i
 
     auto evaluate = [&](const double* dXc, int64_t rows, double* dF) -> int {
         normalize_kernel<<<unsigned((rows * d + 255) / 256), 256, 0, s>>>(dXc, bXl.as<double>(), bXu.as<double>(), rows, d, bXn.as<double>());
-        return aoed_gp_eval_device(gp, rows, bXn.as<double>(), flags, acq_kind, h_acq_param, nullptr, nullptr, nullptr, nullptr,
-                                   nullptr, nullptr, dF, nullptr, nullptr, s);
+        return eval_fn(s, bXn.as<double>(), rows, dF);
     };
     // rank + crowding of `n` individuals whose objectives are Fa (first na rows) and Fb; keeps the best `keep` in buffer `dst`
     auto survive = [&](int src, int na, const double* Xb, const double* Fb, const uint8_t* dup, int nb, int keep, int dst) -> int {
@@ -394,4 +399,53 @@ extern "C" int aoed_nsga2_run(aoed_gp_t* gp, int device, int n_var, int n_obj, i
     *h_n_out = n_cur;
     if (h_n_eval) *h_n_eval = evals + int64_t(off_evals);
     return AOED_OK;
+}
+
+}  // namespace
+
+extern "C" int aoed_nsga2_run(aoed_gp_t* gp, int device, int n_var, int n_obj, int acq_kind, const double* h_acq_param,
+                              int64_t n_init, const double* h_X0, const double* h_xl, const double* h_xu, int pop_size,
+                              int n_gen, uint64_t seed, double* h_X, double* h_F, int64_t* h_n_out, int64_t* h_n_eval) {
+    if (!gp) return nfail(AOED_ERR_INVALID, "null handle");
+    if (acq_kind < AOED_ACQ_IDENTITY || acq_kind > AOED_ACQ_PI) return nfail(AOED_ERR_INVALID, "an acquisition kind is required");
+    const uint32_t flags = acq_kind >= AOED_ACQ_UCB ? AOED_EVAL_STD : 0u;
+    Evaluator ev = [=](cudaStream_t s, const double* dXn, int64_t rows, double* dF) -> int {
+        return aoed_gp_eval_device(gp, rows, dXn, flags, acq_kind, h_acq_param, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                   dF, nullptr, nullptr, s);
+    };
+    return nsga2_core(device, n_var, n_obj, ev, n_init, h_X0, h_xl, h_xu, pop_size, n_gen, seed, h_X, h_F, h_n_out, h_n_eval);
+}
+
+extern "C" int aoed_nsga2_run_rff(int device, int n_var, int n_obj, int n_feat, const double* h_W, const double* h_b,
+                                  const double* h_theta, const double* h_factor, const double* h_y_mean, const double* h_y_scale,
+                                  int64_t n_init, const double* h_X0, const double* h_xl, const double* h_xu, int pop_size,
+                                  int n_gen, uint64_t seed, double* h_X, double* h_F, int64_t* h_n_out, int64_t* h_n_eval) {
+    if (!h_W || !h_b || !h_theta || !h_factor || !h_y_mean || !h_y_scale || n_feat < 1 || n_var < 1 || n_var > NS_MAX_D)
+        return nfail(AOED_ERR_INVALID, "bad argument");
+    if (rff_smem_bytes(n_feat, rff_dp(n_var)) > 200 * 1024) return nfail(AOED_ERR_UNSUPPORTED, "too many spectral points for shared memory");
+    DeviceGuard guard_(device);
+    NCU(guard_.err);
+    const size_t d = n_var, m = n_obj, M = n_feat;
+    NBuf par;
+    NCU(cudaMalloc(&par.p, (m * M * d + 2 * m * M + 3 * m) * sizeof(double)));
+    double* P = par.as<double>();
+    RffArgs base;
+    base.W = P; base.b = P + m * M * d; base.theta = base.b + m * M; base.factor = base.theta + m * M;
+    base.y_mean = base.factor + m; base.y_scale = base.y_mean + m;
+    NCU(cudaMemcpy(const_cast<double*>(base.W), h_W, m * M * d * sizeof(double), cudaMemcpyHostToDevice));
+    NCU(cudaMemcpy(const_cast<double*>(base.b), h_b, m * M * sizeof(double), cudaMemcpyHostToDevice));
+    NCU(cudaMemcpy(const_cast<double*>(base.theta), h_theta, m * M * sizeof(double), cudaMemcpyHostToDevice));
+    NCU(cudaMemcpy(const_cast<double*>(base.factor), h_factor, m * sizeof(double), cudaMemcpyHostToDevice));
+    NCU(cudaMemcpy(const_cast<double*>(base.y_mean), h_y_mean, m * sizeof(double), cudaMemcpyHostToDevice));
+    NCU(cudaMemcpy(const_cast<double*>(base.y_scale), h_y_scale, m * sizeof(double), cudaMemcpyHostToDevice));
+    base.dF = base.hF = nullptr;
+    base.d = n_var; base.m = n_obj; base.M = n_feat;
+    Evaluator ev = [=](cudaStream_t s, const double* dXn, int64_t rows, double* dF) -> int {
+        RffArgs a = base;
+        a.X = dXn; a.F = dF; a.rows = rows;
+        cudaError_t e = rff_launch_value(a, s);
+        if (e != cudaSuccess) return nfail(AOED_ERR_CUDA, std::string("rff_kernel: ") + cudaGetErrorString(e));
+        return AOED_OK;
+    };
+    return nsga2_core(device, n_var, n_obj, ev, n_init, h_X0, h_xl, h_xu, pop_size, n_gen, seed, h_X, h_F, h_n_out, h_n_eval);
 }

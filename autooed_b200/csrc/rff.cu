@@ -12,10 +12,13 @@
 
 #include "../../include/aoed_b200.h"
 #include "common.cuh"
+#include "rff.cuh"
 
 extern "C" int aoed_detail_fail(int code, const char* msg);
 
 namespace {
+
+using namespace aoed;
 
 int rfail(int code, const std::string& msg) { return aoed_detail_fail(code, msg.c_str()); }
 #define RCU(call)                                                                                                    \
@@ -25,89 +28,6 @@ int rfail(int code, const std::string& msg) { return aoed_detail_fail(code, msg.
             return rfail(AOED_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + \
                                             std::to_string(__LINE__));                                               \
     } while (0)
-
-struct RffArgs {
-    const double* X;       // [rows][d] normalised candidates
-    const double* W;       // [m][M][d]
-    const double* b;       // [m][M]
-    const double* theta;   // [m][M]
-    const double* factor;  // [m]  sqrt(2 sf2 / M)
-    const double* y_mean;  // [m]
-    const double* y_scale; // [m]
-    double *F, *dF, *hF;   // (rows, m), (rows, m, d), (rows, m, d, d); any may be null
-    int64_t rows;
-    int d, m, M;
-};
-
-template <int DP, bool GRAD>
-__global__ void __launch_bounds__(128) rff_kernel(RffArgs p) {
-    extern __shared__ double rff_smem[];  // [M][DP] W (zero padded), [M] b, [M] theta
-    const int o = blockIdx.y, d = p.d, M = p.M;
-    double* sW = rff_smem;
-    double* sb = sW + size_t(M) * DP;
-    double* st = sb + M;
-    for (int i = threadIdx.x; i < M * DP; i += 128) {
-        const int j = i / DP, k = i % DP;
-        sW[i] = k < d ? p.W[(int64_t(o) * M + j) * d + k] : 0.0;
-    }
-    for (int j = threadIdx.x; j < M; j += 128) {
-        sb[j] = p.b[int64_t(o) * M + j];
-        st[j] = p.theta[int64_t(o) * M + j];
-    }
-    __syncthreads();
-    const int64_t c = blockIdx.x * int64_t(128) + threadIdx.x;
-    if (c >= p.rows) return;
-    double x[DP];
-#pragma unroll
-    for (int k = 0; k < DP; ++k) x[k] = k < d ? p.X[c * d + k] : 0.0;
-    double f = 0.0, g[GRAD ? DP : 1];
-    if (GRAD) {
-#pragma unroll
-        for (int k = 0; k < DP; ++k) g[k] = 0.0;
-    }
-    for (int j = 0; j < M; ++j) {
-        const double* w = sW + size_t(j) * DP;
-        double t = sb[j];
-#pragma unroll
-        for (int k = 0; k < DP; ++k) t = fma(w[k], x[k], t);
-        double sn, cs;
-        sincos(t, &sn, &cs);
-        const double th = st[j];
-        f = fma(th, cs, f);
-        if (GRAD) {
-            const double q = th * sn;
-#pragma unroll
-            for (int k = 0; k < DP; ++k) g[k] = fma(q, w[k], g[k]);
-        }
-    }
-    const double fac = p.factor[o], ys = p.y_scale[o];
-    if (p.F) p.F[c * p.m + o] = fma(fac * f, ys, p.y_mean[o]);  // normalization.undo (ts.py:83)
-    if (GRAD && p.dF) {
-#pragma unroll
-        for (int k = 0; k < DP; ++k)
-            if (k < d) p.dF[(c * p.m + o) * d + k] = -fac * g[k] * ys;  // ts.py:74, rescale ts.py:84
-    }
-}
-
-__global__ void __launch_bounds__(256) rff_hess_kernel(RffArgs p) {
-    extern __shared__ double hs_smem[];  // [M] theta_j cos(t_j)
-    const int64_t c = blockIdx.x;
-    const int o = blockIdx.y, d = p.d, M = p.M;
-    const double* W = p.W + int64_t(o) * M * d;
-    for (int j = threadIdx.x; j < M; j += 256) {
-        double t = p.b[int64_t(o) * M + j];
-        for (int k = 0; k < d; ++k) t = fma(W[int64_t(j) * d + k], p.X[c * d + k], t);
-        hs_smem[j] = p.theta[int64_t(o) * M + j] * cos(t);
-    }
-    __syncthreads();
-    const double fac = p.factor[o];
-    for (int pr = threadIdx.x; pr < d * d; pr += 256) {
-        const int i = pr / d, k = pr % d;
-        double s = 0.0;
-        for (int j = 0; j < M; ++j) s = fma(hs_smem[j] * W[int64_t(j) * d + i], W[int64_t(j) * d + k], s);
-        p.hF[((c * p.m + o) * d + i) * d + k] = -fac * s;  // ts.py:77 (not rescaled: literal)
-    }
-}
 
 struct DBuf {
     void* p = nullptr;

@@ -161,9 +161,14 @@ def device_nsga2(acquisition, X0, xl, xu, pop_size, n_gen, seed):
     param = None if param is None else _lib.as_f64(param)
     Xo, Fo = np.empty((pop_size, d)), np.empty((pop_size, m))
     n_out, n_eval = ctypes.c_int64(), ctypes.c_int64()
-    _lib.check(lib.aoed_nsga2_run(h, sm.device, d, m, acquisition.kind, _lib.ptr(param), X0.shape[0], _lib.ptr(X0),
-                                  _lib.ptr(_lib.as_f64(xl)), _lib.ptr(_lib.as_f64(xu)), pop_size, n_gen, seed, _lib.ptr(Xo),
-                                  _lib.ptr(Fo), ctypes.byref(n_out), ctypes.byref(n_eval)))
+    tail = (X0.shape[0], _lib.ptr(X0), _lib.ptr(_lib.as_f64(xl)), _lib.ptr(_lib.as_f64(xu)), pop_size, n_gen, seed, _lib.ptr(Xo),
+            _lib.ptr(Fo), ctypes.byref(n_out), ctypes.byref(n_eval))
+    if hasattr(acquisition, 'device_sample'):  # Thompson sampling: the loop evaluates the random-Fourier-feature sample
+        W, b, theta, factor, y_mean, y_scale = acquisition.device_sample()
+        _lib.check(lib.aoed_nsga2_run_rff(sm.device, d, m, W.shape[1], _lib.ptr(W), _lib.ptr(b), _lib.ptr(theta), _lib.ptr(factor),
+                                          _lib.ptr(y_mean), _lib.ptr(y_scale), *tail))
+    else:
+        _lib.check(lib.aoed_nsga2_run(h, sm.device, d, m, acquisition.kind, _lib.ptr(param), *tail))
     return Xo[:n_out.value], Fo[:n_out.value], n_eval.value
 
 
@@ -184,7 +189,8 @@ class NSGA2(Solver):
         acq = self.problem.acquisition
         sm = getattr(acq, 'surrogate_model', None)
         return (self.on_device and getattr(self.real_problem, 'n_constr', 0) == 0
-                and getattr(acq, 'kind', _lib.ACQ_NONE) != _lib.ACQ_NONE and not getattr(acq, 'exact', False)
+                and (getattr(acq, 'kind', _lib.ACQ_NONE) != _lib.ACQ_NONE or hasattr(acq, 'device_sample'))
+                and not getattr(acq, 'exact', False)
                 and hasattr(sm, '_ensure_handle') and sm.n_var <= 32 and sm.n_obj <= 8
                 and max(n_init, self.algo.pop_size) + self.algo.pop_size <= 4096)
 

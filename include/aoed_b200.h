@@ -130,6 +130,13 @@ int aoed_nsga2_run(aoed_gp_t* gp, int device, int n_var, int n_obj, int acq_kind
                    const double* h_X0, const double* h_xl, const double* h_xu, int pop_size, int n_gen, uint64_t seed,
                    double* h_X, double* h_F, int64_t* h_n_out, int64_t* h_n_eval);
 
+/* the same loop on a Thompson-sampling posterior sample (arguments as aoed_rff_eval): lets TSEMO, the reference's default
+ * algorithm ('gp' + 'ts' + 'nsga2' + 'hvi'), run its solver step on the device as well. */
+int aoed_nsga2_run_rff(int device, int n_var, int n_obj, int n_feat, const double* h_W, const double* h_b, const double* h_theta,
+                       const double* h_factor, const double* h_y_mean, const double* h_y_scale, int64_t n_init,
+                       const double* h_X0, const double* h_xl, const double* h_xu, int pop_size, int n_gen, uint64_t seed,
+                       double* h_X, double* h_F, int64_t* h_n_out, int64_t* h_n_eval);
+
 /* ---- Thompson-sampling acquisition -----------------------------------------------
  * replaces ThompsonSampling._evaluate (autooed/mobo/acquisition/ts.py:65-87) incl. its un-normalisation: value, gradient
  * and Hessian of the random-Fourier-feature posterior sample  f_o(x) = factor_o * sum_j theta_oj cos(W_oj . x + b_oj).

@@ -78,6 +78,21 @@ def test_first_generation_only_and_fallbacks():
     ts = ab.ThompsonSampling(sur)
     np.random.seed(0)
     ts.fit(X, Y)
-    s = NSGA2(prob, n_gen=5, pop_size=40)
-    Xt, Ft = s.solve(X, Y, 8, ts)  # no fused device acquisition for Thompson sampling: host loop, device evaluations
-    assert Xt.shape == (40, 6) and not s._device_eligible(48)
+    s = NSGA2(prob, n_gen=30, pop_size=40)
+    np.random.seed(1)
+    Xt, Ft = s.solve(X, Y, 8, ts)  # Thompson sampling: the device loop evaluates the random-Fourier-feature sample
+    assert Xt.shape == (40, 6) and s._device_eligible(48)
+    F2, _, _ = ts.evaluate(Xt)
+    assert np.allclose(Ft, F2, rtol=1e-11, atol=1e-12)
+    np.random.seed(1)
+    Xh, Fh = NSGA2(prob, n_gen=30, pop_size=40, on_device=False).solve(X, Y, 8, ts)  # host loop, same acquisition
+    ref = np.maximum(Ft.max(0), Fh.max(0)) + 0.1
+    assert mo.hypervolume(Ft, ref) > 0.9 * mo.hypervolume(Fh, ref)
+
+    class Constrained(type(prob)):
+        def evaluate_constraint(self, x):
+            return np.array([x[0] - 0.9])
+    cprob = Constrained(6, 2, n_constr=1)
+    sc = NSGA2(cprob, n_gen=3, pop_size=20)
+    Xc2, _ = sc.solve(X, Y, 4, acq)  # constraints are evaluated by the real problem on the host: host loop
+    assert Xc2.shape == (20, 6) and not sc._device_eligible(44)
