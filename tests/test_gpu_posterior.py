@@ -304,3 +304,35 @@ def test_exact_hessian_vs_oracle_and_fd(nu, shape, monkeypatch):
             om = gp._evaluate(Xs[:4] - e, True, True, False)
             assert np.allclose((op["dF"] - om["dF"]) / (2 * h), out["hF"][:, :, :, k], rtol=1e-4, atol=1e-5 * np.abs(out["hF"]).max())
             assert np.allclose((op["dS"] - om["dS"]) / (2 * h), out["hS"][:, :, :, k], rtol=1e-3, atol=1e-4 * np.abs(out["hS"]).max())
+
+
+@pytest.mark.parametrize("N", [2, 15, 16, 17, 127, 128, 129, 255, 256, 257, 511, 513, 1025])
+def test_tile_boundaries_vs_oracle(N):
+    """Training-set sizes around every tiling boundary of the triangular products (k-step 16, row tile 128, sum-of-squares
+    slices of 32 rows) and candidate counts around the 128-column tile, std + gradient + literal Hessian."""
+    from autooed_b200 import GaussianProcess
+    from autooed_b200.problem import SimpleProblem
+    d, m = 5, 2
+    rng = np.random.default_rng(1000 + N)
+    X = rng.random((N, d))
+    Y = np.sin(X @ rng.standard_normal((d, m))) + 0.05 * rng.standard_normal((N, m))
+    thetas = np.stack([np.concatenate([[0.2], rng.uniform(-0.8, 0.3, d), [-4.0]]) for _ in range(m)])
+    gp = GaussianProcess(SimpleProblem(d, m), nu=3)
+    gp.fit_fixed(X, Y, thetas)
+    orc = go.GPOracle(d, m, nu=3).fit(X, Y, thetas=thetas)
+    cond = max(np.linalg.cond(st.L) ** 2 for st in orc.states)
+    tol = max(1e-8, 100 * cond * EPS)
+    prior = np.exp(thetas[:, 0]) + np.exp(thetas[:, -1])
+    for C in (1, 127, 129):
+        Xs = rng.random((C, d))
+        out = gp.evaluate(Xs, std=True, gradient=True, hessian=C == 1)
+        ref = orc.evaluate(Xs, std=True, gradient=True, hessian=C == 1, var_form="chol")
+        assert rel(out["F"], ref["F"]) < tol and rel(out["dF"], ref["dF"]) < tol
+        dv = np.abs((out["S"] / orc.norm.y_scale) ** 2 - (ref["S"] / orc.norm.y_scale) ** 2) / prior
+        assert dv.max() < max(1e-10, tol * 1e-2)
+        ok = ((ref["S"] / orc.norm.y_scale) ** 2 / prior > 1e-6).all(axis=1)
+        if ok.any():
+            assert rel(out["dS"][ok], ref["dS"][ok]) < max(1e-7, tol * 10)
+            if C == 1:
+                assert rel(out["hF"], ref["hF"]) < tol
+                assert rel(out["hS"][ok], ref["hS"][ok]) < max(1e-6, tol * 100)
