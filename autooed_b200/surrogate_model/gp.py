@@ -17,6 +17,14 @@ from scipy.optimize import minimize
 from autooed_b200 import _lib
 from autooed_b200.surrogate_model.base import SurrogateModel
 
+try:  # the optimiser's own linear algebra is tiny (p = n_var + 2): keep a many-threaded BLAS from spinning on it
+    from threadpoolctl import threadpool_limits as _blas_threads
+except ImportError:  # pragma: no cover
+    import contextlib
+
+    def _blas_threads(limits=None):
+        return contextlib.nullcontext()
+
 
 def initial_theta(n_var):
     """log[c1=1, l=1..1, c2=1e-2]  (gp.py:126-132)."""
@@ -234,11 +242,12 @@ class GaussianProcess(SurrogateModel):
                 pool.finish(b)
 
         threads = [threading.Thread(target=worker, args=(b,), daemon=True) for b in range(len(problems))]
-        for t in threads:
-            t.start()
-        pool.serve()
-        for t in threads:
-            t.join()
+        with _blas_threads(limits=1):
+            for t in threads:
+                t.start()
+            pool.serve()
+            for t in threads:
+                t.join()
         for r in results:
             if isinstance(r, BaseException):
                 raise r

@@ -438,6 +438,25 @@ class _OracleAcquisition:
         return go.acquisition(self.kind, val, gradient, hessian, n_sample=self.n_sample, y_min=self.y_min)
 
 
+class _OracleTS:
+    """Thompson-sampling acquisition on the CPU (oracle/ts_oracle.py restates acquisition/ts.py)."""
+
+    def __init__(self, surrogate):
+        self.s, self.fitted = surrogate, False
+
+    def fit(self, X, Y):
+        from oracle import ts_oracle as to
+        orc = self.s.orc
+        Xn, Yn = orc.norm.do_x(np.asarray(X, float)), orc.norm.do_y(np.asarray(Y, float))
+        self.sample = to.ts_fit(Xn, Yn, [st.theta for st in orc.states], self.s.nu)
+        self.fitted = True
+
+    def evaluate(self, X, dtype='continuous', gradient=False, hessian=False):
+        from oracle import ts_oracle as to
+        orc = self.s.orc
+        return to.ts_evaluate(orc.norm.do_x(np.atleast_2d(X)), *self.sample, orc.norm.y_mean, orc.norm.y_scale, gradient, hessian)
+
+
 class _OracleHVI:
     def select(self, X_candidate, Y_candidate, X, Y, batch_size):
         from oracle import moo_oracle as mo
@@ -465,9 +484,10 @@ def _dtlz2(X, m=3):
 def run_mobo_mode(args):
     """MOBO iteration wall time: fit + acquisition.fit + NSGA-II solve + HVI select per iteration on the
     BASELINE configs c1 (ZDT1 d=6 m=2, identity acquisition, pop 200 x 200 generations, batch 10) and c2 (DTLZ2 d=10 m=3,
-    EI, pop 1000, batch 20): B200 path vs the CPU port with the same solver code and seeds."""
+    EI, pop 1000, batch 20), plus TSEMO (the reference's CLI default: Thompson sampling + NSGA-II + HVI) on the c1 problem:
+    B200 path vs the CPU port (host NSGA-II with the same operators, same seeds)."""
     import random
-    from autooed_b200 import (ExpectedImprovement, GaussianProcess, HypervolumeImprovement, Identity)
+    from autooed_b200 import (ExpectedImprovement, GaussianProcess, HypervolumeImprovement, Identity, ThompsonSampling)
     from autooed_b200.mobo import MOBO
     from autooed_b200.problem import SimpleProblem
     from autooed_b200.solver import NSGA2
@@ -475,7 +495,9 @@ def run_mobo_mode(args):
     from autooed_b200.utils.pareto import calc_hypervolume
     from oracle import moo_oracle as mo
     ctx, threads = blas_threads()
-    configs = [dict(name="c1", f=_zdt1, d=6, m=2, nu=1, acq="identity", pop=200, gens=200, batch=10, n_init=20,
+    configs = [dict(name="tsemo-default", f=_zdt1, d=6, m=2, nu=1, acq="ts", pop=200, gens=200, batch=10, n_init=20,
+                    iters=args.mobo_iters, cpu_iters=min(args.mobo_iters, 3)),
+               dict(name="c1", f=_zdt1, d=6, m=2, nu=1, acq="identity", pop=200, gens=200, batch=10, n_init=20,
                     iters=args.mobo_iters, cpu_iters=min(args.mobo_iters, 3)),
                dict(name="c2", f=lambda X: _dtlz2(X, 3), d=10, m=3, nu=1, acq="ei", pop=1000, gens=200, batch=20, n_init=30,
                     iters=max(2, args.mobo_iters // 4), cpu_iters=1)]
@@ -488,12 +510,12 @@ def run_mobo_mode(args):
             Y = c["f"](X)
             if arm == "b200":
                 sur = GaussianProcess(prob, nu=c["nu"])
-                acq = (Identity if c["acq"] == "identity" else ExpectedImprovement)(sur)
+                acq = {"identity": Identity, "ei": ExpectedImprovement, "ts": ThompsonSampling}[c["acq"]](sur)
                 opt = MOBO(prob, sur, acq, NSGA2(prob, n_gen=c["gens"], pop_size=c["pop"]), HypervolumeImprovement(sur))
                 n_it = c["iters"]
             else:
                 sur = _OracleSurrogate(prob, c["nu"])
-                acq = _OracleAcquisition(sur, c["acq"])
+                acq = _OracleTS(sur) if c["acq"] == "ts" else _OracleAcquisition(sur, c["acq"])
                 opt = MOBO(prob, sur, acq, NSGA2(prob, n_gen=c["gens"], pop_size=c["pop"], rank_fn=mo.pareto_rank), _OracleHVI())
                 n_it = c["cpu_iters"]
             # where the iteration goes: surrogate fit, acquisition calls + non-dominated sorting inside the solver, selection
