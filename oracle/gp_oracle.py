@@ -470,3 +470,43 @@ class GPOracle:
             if std:
                 out["hS"] = out["hS"] * self.norm.y_scale[None, :, None, None]
         return out
+
+
+# --------------------------------------------------------------------------------------
+# extended-precision ground truth for the posterior variance
+# --------------------------------------------------------------------------------------
+def variance_truth_longdouble(theta, X, Xs, nu):
+    """sigma^2 = k** - |L^-1 k*|^2 with kernel matrix, Cholesky factorisation and forward substitution carried out in
+    numpy longdouble (80-bit on x86-64) — the yardstick for 'whose variance is closer to the truth' comparisons
+    (gp.py:154-165 loses digits through the explicit inverse when cond(K) is large)."""
+    ld = np.longdouble
+    c1, ell, c2 = _split_theta(theta)
+    c1, c2, ell = ld(c1), ld(c2), ell.astype(ld)
+    A, B = X.astype(ld) / ell, Xs.astype(ld) / ell
+
+    def kern(P, Q):
+        r = np.sqrt(((P[:, None, :] - Q[None, :, :]) ** 2).sum(-1))
+        s3, s5 = np.sqrt(ld(3)), np.sqrt(ld(5))
+        if nu == 1:
+            phi = np.exp(-r)
+        elif nu == 3:
+            phi = (1 + s3 * r) * np.exp(-s3 * r)
+        elif nu == 5:
+            phi = (1 + s5 * r + 5 * r * r / 3) * np.exp(-s5 * r)
+        else:
+            phi = np.exp(-r * r / 2)
+        return c1 * phi + c2
+
+    n = len(X)
+    K = kern(A, A)
+    K[np.diag_indices(n)] = c1 + c2 + ld(JITTER)
+    L = np.zeros((n, n), dtype=ld)
+    for j in range(n):
+        L[j, j] = np.sqrt(K[j, j] - (L[j, :j] ** 2).sum())
+        if j + 1 < n:
+            L[j + 1:, j] = (K[j + 1:, j] - L[j + 1:, :j] @ L[j, :j]) / L[j, j]
+    ks = kern(B, A)  # (C, n)
+    w = np.zeros_like(ks)
+    for i in range(n):
+        w[:, i] = (ks[:, i] - w[:, :i] @ L[i, :i]) / L[i, i]
+    return ((c1 + c2) - (w ** 2).sum(axis=1)).astype(np.float64)
