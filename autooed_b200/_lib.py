@@ -46,6 +46,7 @@ SIGNATURES = {
     "aoed_nsga2_run_rff": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 6 +
                            [ctypes.c_int64, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, _vp, _vp,
                             ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "aoed_nsga2_survival": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, _vp, ctypes.c_int64, _vp, _vp, _vp]),
     "aoed_rff_eval": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 7 +
                       [ctypes.c_uint32, _vp, _vp, _vp]),
     "aoed_pareto_mask": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, _vp, _vp]),

@@ -24,8 +24,6 @@ extern "C" int aoed_detail_fail(int code, const char* msg);  // defined in gp.cu
 
 namespace {
 
-using aoed::rank_small_kernel;
-using aoed::RS_THREADS;
 using aoed::RS_MAX_N;
 
 int mfail(int code, const std::string& msg) { return aoed_detail_fail(code, msg.c_str()); }
@@ -114,19 +112,16 @@ __global__ void rank_update_kernel(int64_t n, const uint8_t* dominated, uint8_t*
     }
 }
 
-int launch_rank_small(int m, const double* YT, int n, int32_t* rank, cudaStream_t s) {
-    const size_t sm = size_t(m) * n * sizeof(double) + 3 * size_t(n) * sizeof(int);
-#define RS_CASE(MM)                                                                                                  \
-    case MM:                                                                                                         \
-        MCU(cudaFuncSetAttribute(rank_small_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));      \
-        rank_small_kernel<MM><<<1, RS_THREADS, sm, s>>>(YT, n, rank);                                                \
+int launch_rank_small(int m, const double* YT, int n, int32_t* rank, int* cnt_scratch, cudaStream_t s) {
+#define RS_CASE(MM)                                                                       \
+    case MM:                                                                              \
+        MCU(aoed::launch_rank_small_m<MM>(YT, n, rank, cnt_scratch, /*need=*/n, s));      \
         break;
     switch (m) {
         RS_CASE(1) RS_CASE(2) RS_CASE(3) RS_CASE(4) RS_CASE(5) RS_CASE(6) RS_CASE(7) RS_CASE(8)
         default: return mfail(AOED_ERR_UNSUPPORTED, "n_obj > 8 is not supported");
     }
 #undef RS_CASE
-    MCU(cudaGetLastError());
     return AOED_OK;
 }
 
@@ -361,10 +356,10 @@ int aoed_pareto_rank(int device, int64_t n, int m, const double* h_Y, int32_t* h
         // one launch, one allocation: the call is latency bound (it runs once per NSGA-II generation)
         Buf d;
         const size_t ybytes = yt.size() * sizeof(double);
-        MCU(cudaMalloc(&d.p, ybytes + size_t(n) * sizeof(int32_t)));
+        MCU(cudaMalloc(&d.p, ybytes + (1 + aoed::DC_SPLIT) * size_t(n) * sizeof(int32_t)));
         MCU(cudaMemcpy(d.p, yt.data(), ybytes, cudaMemcpyHostToDevice));
         int32_t* drank = reinterpret_cast<int32_t*>(static_cast<char*>(d.p) + ybytes);
-        int rc = launch_rank_small(m, d.as<double>(), int(n), drank, nullptr);
+        int rc = launch_rank_small(m, d.as<double>(), int(n), drank, drank + n, nullptr);
         if (rc != AOED_OK) return rc;
         MCU(cudaMemcpy(h_rank, drank, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToHost));
         return AOED_OK;

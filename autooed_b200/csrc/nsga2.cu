@@ -3,7 +3,7 @@
 // Replaces, for the common unconstrained case, the pymoo 0.4.1 `NSGA2` + `minimize(..., ('n_gen', G))` loop that
 // `autooed/mobo/solver/nsga2.py:17-30` drives (one `SurrogateProblem.evaluate` per generation): variation, duplicate
 // elimination, acquisition evaluation, non-dominated sorting, crowding distance and survival all stay on the GPU; the
-// host only enqueues ~8 launches per generation and never synchronises inside the loop.
+// host only enqueues ~12 launches per generation and never synchronises inside the loop.
 //
 // Operators follow pymoo's defaults: binary tournament on (rank, crowding distance), simulated
 // binary crossover (prob 0.9, eta 15, per-variable exchange 0.5), polynomial mutation (eta 20, prob 1/n_var), offspring
@@ -15,6 +15,8 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 #include <climits>
 #include <string>
 #include <vector>
@@ -47,7 +49,6 @@ int nfail(int code, const std::string& msg) { return aoed_detail_fail(code, msg.
     } while (0)
 
 constexpr int NS_MAX_D = 32;
-constexpr int NS_SORT_THREADS = 1024;
 
 struct VarArgs {
     const double* X;      // [n_cur][d] current population (continuous)
@@ -88,39 +89,38 @@ __device__ __forceinline__ double poly_mutate(double x, double lo, double hi, do
     return fmin(fmax(x + dq * span, lo), hi);
 }
 
-// one thread per offspring PAIR: two tournaments per parent, SBX, polynomial mutation
+// one thread per (offspring pair, variable).  The pair-level draws (two tournaments per parent, the crossover coin) sit at
+// the start of the pair's Philox subsequence and are replayed by each of its threads; variable k owns the 64 draws at
+// offset 64 (k + 1) of the same subsequence, so the result does not depend on how the work is spread over threads.
 __global__ void __launch_bounds__(128) variation_kernel(VarArgs p) {
-    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pair = gid / p.d, k = gid - pair * p.d;
     if (2 * pair >= p.P) return;
     curandStatePhilox4_32_10_t st;
-    curand_init(p.seed, (unsigned long long)pair, (unsigned long long)p.gen * 4096ull, &st);
+    const unsigned long long base = (unsigned long long)p.gen * 4096ull;
+    curand_init(p.seed, (unsigned long long)pair, base, &st);
     const int ia = tournament(st, p), ib = tournament(st, p);
-    const double* pa = p.X + int64_t(ia) * p.d;
-    const double* pb = p.X + int64_t(ib) * p.d;
     const bool do_pair = curand_uniform_double(&st) < p.pc;
-    double* c1 = p.Xoff + int64_t(2 * pair) * p.d;
-    double* c2 = (2 * pair + 1 < p.P) ? c1 + p.d : nullptr;
-    const double pm = 1.0 / p.d;
-    for (int k = 0; k < p.d; ++k) {
-        const double lo = p.xl[k], hi = p.xu[k];
-        double x1 = pa[k], x2 = pb[k];
-        const double uv = curand_uniform_double(&st), u = curand_uniform_double(&st), us = curand_uniform_double(&st);
-        if (do_pair && uv < 0.5 && fabs(x1 - x2) > 1e-14) {
-            const double y1 = fmin(x1, x2), y2 = fmax(x1, x2), delta = y2 - y1;
-            const double b1 = sbx_betaq(u, 1.0 + 2.0 * (y1 - lo) / delta, p.eta_c);
-            const double b2 = sbx_betaq(u, 1.0 + 2.0 * (hi - y2) / delta, p.eta_c);
-            const double o1 = fmin(fmax(0.5 * ((y1 + y2) - b1 * delta), lo), hi);
-            const double o2 = fmin(fmax(0.5 * ((y1 + y2) + b2 * delta), lo), hi);
-            x1 = us < 0.5 ? o2 : o1;
-            x2 = us < 0.5 ? o1 : o2;
-        }
-        const double m1 = curand_uniform_double(&st), v1 = curand_uniform_double(&st);
-        const double m2 = curand_uniform_double(&st), v2 = curand_uniform_double(&st);
-        if (m1 < pm) x1 = poly_mutate(x1, lo, hi, v1, p.eta_m);
-        if (m2 < pm) x2 = poly_mutate(x2, lo, hi, v2, p.eta_m);
-        c1[k] = x1;
-        if (c2) c2[k] = x2;
+    curand_init(p.seed, (unsigned long long)pair, base + 64ull * (k + 1), &st);
+    const double lo = p.xl[k], hi = p.xu[k];
+    double x1 = p.X[int64_t(ia) * p.d + k], x2 = p.X[int64_t(ib) * p.d + k];
+    const double uv = curand_uniform_double(&st), u = curand_uniform_double(&st), us = curand_uniform_double(&st);
+    if (do_pair && uv < 0.5 && fabs(x1 - x2) > 1e-14) {
+        const double y1 = fmin(x1, x2), y2 = fmax(x1, x2), delta = y2 - y1;
+        const double b1 = sbx_betaq(u, 1.0 + 2.0 * (y1 - lo) / delta, p.eta_c);
+        const double b2 = sbx_betaq(u, 1.0 + 2.0 * (hi - y2) / delta, p.eta_c);
+        const double o1 = fmin(fmax(0.5 * ((y1 + y2) - b1 * delta), lo), hi);
+        const double o2 = fmin(fmax(0.5 * ((y1 + y2) + b2 * delta), lo), hi);
+        x1 = us < 0.5 ? o2 : o1;
+        x2 = us < 0.5 ? o1 : o2;
     }
+    const double pm = 1.0 / p.d;
+    const double m1 = curand_uniform_double(&st), v1 = curand_uniform_double(&st);
+    const double m2 = curand_uniform_double(&st), v2 = curand_uniform_double(&st);
+    if (m1 < pm) x1 = poly_mutate(x1, lo, hi, v1, p.eta_m);
+    if (m2 < pm) x2 = poly_mutate(x2, lo, hi, v2, p.eta_m);
+    p.Xoff[int64_t(2 * pair) * p.d + k] = x1;
+    if (2 * pair + 1 < p.P) p.Xoff[int64_t(2 * pair + 1) * p.d + k] = x2;
 }
 
 // Xn = clip((X - xl) / (xu - xl), 0, 1): the normalisation SurrogateModel.evaluate applies (utils/normalization.py:31-32)
@@ -132,21 +132,36 @@ __global__ void normalize_kernel(const double* __restrict__ X, const double* __r
     Xn[i] = fmin(fmax((X[i] - xl[k]) / (xu[k] - xl[k]), 0.0), 1.0);
 }
 
-// dup[o] = 1 when offspring o equals (on the 1e-8 grid) a population member or an EARLIER offspring
-__global__ void __launch_bounds__(128) duplicate_kernel(const double* __restrict__ Xpop, int n_cur, const double* __restrict__ Xoff,
-                                                        int P, int d, uint8_t* __restrict__ dup) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+// dup[o] = 1 when offspring o equals (on the 1e-8 grid) a population member or an EARLIER offspring.  The grid value of
+// the first coordinate of every individual is staged in shared memory; one warp per offspring scans it and looks at the
+// other coordinates only where the first one matches.  *n_eval += number of offspring kept.
+constexpr int DUP_WARPS = 8;
+__global__ void __launch_bounds__(32 * DUP_WARPS) duplicate_kernel(const double* __restrict__ Xpop, int n_cur,
+                                                                   const double* __restrict__ Xoff, int P, int d,
+                                                                   uint8_t* __restrict__ dup, unsigned long long* n_eval) {
+    extern __shared__ double dup_key[];  // [n_cur + P]
+    for (int j = threadIdx.x; j < n_cur + P; j += 32 * DUP_WARPS)
+        dup_key[j] = rint((j < n_cur ? Xpop[int64_t(j) * d] : Xoff[int64_t(j - n_cur) * d]) * 1e8);
+    __syncthreads();
+    const int o = blockIdx.x * DUP_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (o >= P) return;
-    double q[NS_MAX_D];
-    for (int k = 0; k < d; ++k) q[k] = rint(Xoff[int64_t(o) * d + k] * 1e8);
-    bool found = false;
-    for (int j = 0; j < n_cur + o && !found; ++j) {
-        const double* x = j < n_cur ? Xpop + int64_t(j) * d : Xoff + int64_t(j - n_cur) * d;
-        bool same = true;
-        for (int k = 0; k < d && same; ++k) same = rint(x[k] * 1e8) == q[k];
-        found = same;
+    const double* xo = Xoff + int64_t(o) * d;
+    const double q0 = dup_key[n_cur + o];
+    const int total = n_cur + o;
+    bool same_any = false;
+    for (int j = lane; j < total; j += 32) {
+        if (dup_key[j] == q0) {  // rare: compare the other coordinates
+            const double* x = j < n_cur ? Xpop + int64_t(j) * d : Xoff + int64_t(j - n_cur) * d;
+            bool same = true;
+            for (int k = 1; k < d && same; ++k) same = rint(x[k] * 1e8) == rint(xo[k] * 1e8);
+            same_any = same_any || same;
+        }
     }
-    dup[o] = found ? 1 : 0;
+    const bool found = __any_sync(0xffffffffu, same_any);
+    if (lane == 0) {
+        dup[o] = found ? 1 : 0;
+        if (!found) atomicAdd(n_eval, 1ull);
+    }
 }
 
 // merged objective-major table YT[k][i] of population (rows < n_cur) and offspring; discarded offspring get +DBL_MAX
@@ -162,112 +177,153 @@ __global__ void merge_kernel(const double* __restrict__ Fpop, int n_cur, const d
     }
 }
 
-// ---- crowding distance + survival in one CTA (n <= 4096) --------------------------------------------------------
-template <class Less>
-__device__ void bitonic_sort(int* idx, int np2, Less less) {
-    for (int k = 2; k <= np2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < np2; t += NS_SORT_THREADS) {
-                const int u = t ^ j;
-                if (u > t) {
-                    const int a = idx[t], b = idx[u];
-                    const bool up = (t & k) == 0;
-                    if (less(b, a) == up) {
-                        idx[t] = b;
-                        idx[u] = a;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-}
+// ---- crowding distance + survival by pairwise counting (no sort, many CTAs) ---------------------------------
+// A warp owns 32 consecutive individuals, the 8 warps of a CTA split the individuals they are compared with, which are
+// staged in shared memory first (see dom_count_kernel).  Individuals ranked above *last_rank (the unpeeled rest of an
+// early-stopped sort) can never survive and are skipped.
+constexpr int CW_WARPS = 16;
+inline size_t crowd_smem(int n) { return size_t(n) * (sizeof(double) + 2 * sizeof(int)); }
 
-struct SurviveArgs {
-    const double* YT;   // [m][n]
-    const int* rank;    // [n]
-    double* crowd;      // [n] scratch / output (crowding distance of every merged individual)
-    int* sel;           // [keep] survivors (indices into the merged table), best first
-    int n, m, keep;
-};
-
-__global__ void __launch_bounds__(NS_SORT_THREADS) survive_kernel(SurviveArgs p) {
-    extern __shared__ int sv_smem[];
-    const int n = p.n;
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    int* idx = sv_smem;          // [np2]
-    int* gstart = idx + np2;     // [n] first sorted position of each rank group
-    int* gend = gstart + n;      // [n] last sorted position of each rank group
-    const int tid = threadIdx.x;
-    for (int i = tid; i < n; i += NS_SORT_THREADS) p.crowd[i] = 0.0;
-    for (int k = 0; k < p.m; ++k) {
-        const double* f = p.YT + int64_t(k) * n;
-        for (int t = tid; t < np2; t += NS_SORT_THREADS) idx[t] = t;  // indices >= n are padding (sorted last)
-        __syncthreads();
-        bitonic_sort(idx, np2, [&](int a, int b) {
-            if (a >= n || b >= n) return a < n && b >= n ? true : (a >= n && b >= n ? a < b : false);
-            const int ra = p.rank[a], rb = p.rank[b];
-            if (ra != rb) return ra < rb;
-            if (f[a] != f[b]) return f[a] < f[b];
-            return a < b;
-        });
-        for (int t = tid; t < n; t += NS_SORT_THREADS) {
-            const int r = p.rank[idx[t]];
-            if (t == 0 || p.rank[idx[t - 1]] != r) gstart[r] = t;
-            if (t == n - 1 || p.rank[idx[t + 1]] != r) gend[r] = t;
+// crowding distance: for every objective the neighbours of i inside its own front in (value, index) order — the
+// order a stable sort gives (pymoo calc_crowding_distance); front boundary -> +inf.  Only the neighbours' VALUES enter
+// the distance, so the scan keeps branch-free running max / min of the values before / after i and counts them.
+__global__ void __launch_bounds__(32 * CW_WARPS) crowd_kernel(const double* __restrict__ YT, const int* __restrict__ rank,
+                                                              const int* __restrict__ last_rank, int n, int m,
+                                                              double* __restrict__ crowd) {
+    extern __shared__ double cw_smem[];
+    double* fs = cw_smem;                           // [nr] objective k of the relevant individuals (rank <= *last_rank)
+    int* rs = reinterpret_cast<int*>(fs + n);       // [nr] their ranks
+    int* js = rs + n;                               // [nr] their indices (any order: the scan only takes max / min / counts)
+    __shared__ double s_pf[CW_WARPS][32], s_nf[CW_WARPS][32], s_lo[CW_WARPS][32], s_hi[CW_WARPS][32];
+    __shared__ int s_np[CW_WARPS][32], s_nn[CW_WARPS][32];
+    __shared__ int n_rel;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = blockIdx.x * 32 + lane;
+    const int last = *last_rank;
+    const int ri = i < n ? rank[i] : INT_MAX;
+    const bool active = i < n && ri <= last;
+    if (threadIdx.x == 0) n_rel = 0;
+    if (__syncthreads_or(active) == 0) {
+        if (w == 0 && i < n) crowd[i] = 0.0;
+        return;
+    }
+    for (int j = threadIdx.x; j < n; j += 32 * CW_WARPS) {
+        const int r = rank[j];
+        if (r <= last) {
+            const int q = atomicAdd(&n_rel, 1);
+            rs[q] = r;
+            js[q] = j;
         }
+    }
+    __syncthreads();
+    const int nr = n_rel;
+    double acc = 0.0;
+    for (int k = 0; k < m; ++k) {
+        const double* f = YT + int64_t(k) * n;
+        for (int q = threadIdx.x; q < nr; q += 32 * CW_WARPS) fs[q] = f[js[q]];
         __syncthreads();
-        for (int t = tid; t < n; t += NS_SORT_THREADS) {
-            const int i = idx[t], r = p.rank[i];
-            const int s = gstart[r], e = gend[r];
-            if (t == s || t == e) {
-                p.crowd[i] = INFINITY;  // boundary points of a front
-            } else {
-                const double span = f[idx[e]] - f[idx[s]];
-                if (span > 0.0 && span < DBL_MAX) p.crowd[i] += (f[idx[t + 1]] - f[idx[t - 1]]) / span;
+        const double fi = active ? f[i] : 0.0;
+        double pf = -INFINITY, nf = INFINITY, lo = INFINITY, hi = -INFINITY;
+        int n_before = 0, n_after = 0;  // members of i's front before / after it in (f, index) order
+        if (active) {
+#pragma unroll 4
+            for (int q = w; q < nr; q += CW_WARPS) {
+                const bool mine = rs[q] == ri;
+                const double fj = fs[q];
+                const int j = js[q];
+                const bool before = mine && (fj < fi || (fj == fi && j < i));
+                const bool after = mine && (fj > fi || (fj == fi && j > i));
+                lo = fmin(lo, mine ? fj : INFINITY);
+                hi = fmax(hi, mine ? fj : -INFINITY);
+                pf = fmax(pf, before ? fj : -INFINITY);
+                nf = fmin(nf, after ? fj : INFINITY);
+                n_before += before ? 1 : 0;
+                n_after += after ? 1 : 0;
             }
+        }
+        s_pf[w][lane] = pf; s_nf[w][lane] = nf; s_lo[w][lane] = lo; s_hi[w][lane] = hi;
+        s_np[w][lane] = n_before; s_nn[w][lane] = n_after;
+        __syncthreads();
+        if (w == 0 && active) {
+            for (int q = 1; q < CW_WARPS; ++q) {
+                pf = fmax(pf, s_pf[q][lane]);
+                nf = fmin(nf, s_nf[q][lane]);
+                lo = fmin(lo, s_lo[q][lane]);
+                hi = fmax(hi, s_hi[q][lane]);
+                n_before += s_np[q][lane];
+                n_after += s_nn[q][lane];
+            }
+            const double span = hi - lo;
+            if (n_before == 0 || n_after == 0) acc = INFINITY;
+            else if (span > 0.0 && span < DBL_MAX) acc += (nf - pf) / span;
         }
         __syncthreads();
     }
-    // survival: fronts in order, inside a front the lonelier individual first
-    for (int t = tid; t < np2; t += NS_SORT_THREADS) idx[t] = t;
-    __syncthreads();
-    bitonic_sort(idx, np2, [&](int a, int b) {
-        if (a >= n || b >= n) return a < n && b >= n ? true : (a >= n && b >= n ? a < b : false);
-        const int ra = p.rank[a], rb = p.rank[b];
-        if (ra != rb) return ra < rb;
-        const double ca = p.crowd[a], cb = p.crowd[b];
-        if (ca != cb) return ca > cb;
-        return a < b;
-    });
-    for (int t = tid; t < p.keep; t += NS_SORT_THREADS) p.sel[t] = idx[t];
+    if (w == 0 && i < n) crowd[i] = active ? acc : 0.0;
 }
 
-// new population = merged[sel]
-__global__ void gather_kernel(const double* __restrict__ Xpop, const double* __restrict__ Fpop, int n_cur, const double* __restrict__ Xoff,
-                              const double* __restrict__ Foff, const int* __restrict__ rank, const double* __restrict__ crowd,
-                              const int* __restrict__ sel, int keep, int d, int m, double* __restrict__ Xnew, double* __restrict__ Fnew,
-                              int* __restrict__ rnew, double* __restrict__ cnew) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= keep) return;
-    const int i = sel[t];
-    const double* x = i < n_cur ? Xpop + int64_t(i) * d : Xoff + int64_t(i - n_cur) * d;
-    const double* f = i < n_cur ? Fpop + int64_t(i) * m : Foff + int64_t(i - n_cur) * m;
-    for (int k = 0; k < d; ++k) Xnew[int64_t(t) * d + k] = x[k];
-    for (int k = 0; k < m; ++k) Fnew[int64_t(t) * m + k] = f[k];
-    rnew[t] = rank[i];
-    cnew[t] = crowd[i];
-}
+// survivors: position of i in the order (rank, crowding distance descending, index) = number of individuals before it;
+// the individuals whose position is below `keep` are copied to that row of the next population
+struct SelectArgs {
+    const int* rank;         // [n] merged table
+    const double* crowd;     // [n]
+    const int* last_rank;
+    const double *Xpop, *Fpop, *Xoff, *Foff;  // merged table = population rows [0, n_cur) then offspring rows
+    int n, n_cur, keep, d, m;
+    int* sel;                // [keep] survivors' indices in the merged table, best first
+    double *Xnew, *Fnew, *cnew;
+    int* rnew;
+};
 
-__global__ void count_valid_kernel(const uint8_t* dup, int P, unsigned long long* n_eval) {
-    __shared__ unsigned int c;
-    if (threadIdx.x == 0) c = 0;
+__global__ void __launch_bounds__(32 * CW_WARPS) select_kernel(SelectArgs p) {
+    extern __shared__ double cw_smem[];
+    const int n = p.n;
+    double* cs = cw_smem;                      // [nr] crowding distances of the relevant individuals
+    int* rs = reinterpret_cast<int*>(cs + n);  // [nr] ranks
+    int* js = rs + n;                          // [nr] indices
+    __shared__ int part[32];
+    __shared__ int n_rel;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = blockIdx.x * 32 + lane;
+    const int last = *p.last_rank;
+    const int ri = i < n ? p.rank[i] : INT_MAX;
+    const bool active = i < n && ri <= last;
+    if (threadIdx.x == 0) n_rel = 0;
+    if (__syncthreads_or(active) == 0) return;
+    for (int j = threadIdx.x; j < n; j += 32 * CW_WARPS) {
+        const int r = p.rank[j];
+        if (r <= last) {
+            const int q = atomicAdd(&n_rel, 1);
+            rs[q] = r;
+            js[q] = j;
+            cs[q] = p.crowd[j];
+        }
+    }
+    if (w == 0) part[lane] = 0;
     __syncthreads();
-    unsigned int mine = 0;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) mine += dup[i] ? 0 : 1;
-    atomicAdd(&c, mine);
+    const int nr = n_rel;
+    const double ci = active ? p.crowd[i] : 0.0;
+    if (active) {
+        int c = 0;
+#pragma unroll 4
+        for (int q = w; q < nr; q += CW_WARPS) {
+            const int rj = rs[q], j = js[q];
+            const double cj = cs[q];
+            c += (rj != ri ? rj < ri : (cj != ci ? cj > ci : j < i)) ? 1 : 0;
+        }
+        atomicAdd(&part[lane], c);
+    }
     __syncthreads();
-    if (threadIdx.x == 0) *n_eval += c;
+    if (w == 0 && active && part[lane] < p.keep) {
+        const int t = part[lane];
+        p.sel[t] = i;
+        if (p.Xnew) {
+            const double* x = i < p.n_cur ? p.Xpop + int64_t(i) * p.d : p.Xoff + int64_t(i - p.n_cur) * p.d;
+            const double* f = i < p.n_cur ? p.Fpop + int64_t(i) * p.m : p.Foff + int64_t(i - p.n_cur) * p.m;
+            for (int k = 0; k < p.d; ++k) p.Xnew[int64_t(t) * p.d + k] = x[k];
+            for (int k = 0; k < p.m; ++k) p.Fnew[int64_t(t) * p.m + k] = f[k];
+            p.rnew[t] = ri;
+            p.cnew[t] = ci;
+        }
+    }
 }
 
 struct NBuf {
@@ -279,31 +335,29 @@ struct NBuf {
     T* as() { return static_cast<T*>(p); }
 };
 
-template <int M>
-int launch_rank_m(const double* YT, int n, int32_t* rank, cudaStream_t s) {
-    const size_t sm = rank_small_smem(M, n);
-    NCU(cudaFuncSetAttribute(rank_small_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
-    rank_small_kernel<M><<<1, RS_THREADS, sm, s>>>(YT, n, rank);
-    return AOED_OK;
-}
-
-int launch_rank(int m, const double* YT, int n, int32_t* rank, cudaStream_t s) {
+int launch_rank(int m, const double* YT, int n, int32_t* rank, int* cnt_scratch, int need, int* last_rank, cudaStream_t s) {
+#define NS_RANK_CASE(MM)                                                              \
+    case MM:                                                                          \
+        NCU(launch_rank_small_m<MM>(YT, n, rank, cnt_scratch, need, s, last_rank));   \
+        break;
     switch (m) {
-        case 1: return launch_rank_m<1>(YT, n, rank, s);
-        case 2: return launch_rank_m<2>(YT, n, rank, s);
-        case 3: return launch_rank_m<3>(YT, n, rank, s);
-        case 4: return launch_rank_m<4>(YT, n, rank, s);
-        case 5: return launch_rank_m<5>(YT, n, rank, s);
-        case 6: return launch_rank_m<6>(YT, n, rank, s);
-        case 7: return launch_rank_m<7>(YT, n, rank, s);
-        case 8: return launch_rank_m<8>(YT, n, rank, s);
+        NS_RANK_CASE(1) NS_RANK_CASE(2) NS_RANK_CASE(3) NS_RANK_CASE(4) NS_RANK_CASE(5) NS_RANK_CASE(6) NS_RANK_CASE(7) NS_RANK_CASE(8)
         default: return nfail(AOED_ERR_UNSUPPORTED, "n_obj > 8 is not supported");
     }
+#undef NS_RANK_CASE
+    return AOED_OK;
 }
 
 }  // namespace
 
 namespace {
+
+// opt-in to the shared memory the staging kernels need for n individuals (above the 48 KB default from n ~ 4000)
+int set_survival_smem(int n) {
+    NCU(cudaFuncSetAttribute(crowd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(crowd_smem(n))));
+    NCU(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(crowd_smem(n))));
+    return AOED_OK;
+}
 
 // evaluator: (stream, normalised candidates [rows][d] on the device, rows, output [rows][m] on the device) -> rc
 using Evaluator = std::function<int(cudaStream_t, const double*, int64_t, double*)>;
@@ -326,7 +380,7 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
         cudaStream_t s;
         ~StreamGuard() { cudaStreamDestroy(s); }
     } sguard{s};
-    NBuf bX[2], bF[2], bR[2], bC[2], bXoff, bXn, bFoff, bDup, bYT, bRank, bCrowd, bSel, bXl, bXu, bEval;
+    NBuf bX[2], bF[2], bR[2], bC[2], bXoff, bXn, bFoff, bDup, bYT, bRank, bCrowd, bSel, bXl, bXu, bEval, bCnt, bLast;
     for (int i = 0; i < 2; ++i) {
         NCU(cudaMalloc(&bX[i].p, size_t(cap) * d * sizeof(double)));
         NCU(cudaMalloc(&bF[i].p, size_t(cap) * m * sizeof(double)));
@@ -340,6 +394,7 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
     NCU(cudaMalloc(&bYT.p, size_t(cap + P) * m * sizeof(double)));
     NCU(cudaMalloc(&bRank.p, size_t(cap + P) * sizeof(int)));
     NCU(cudaMalloc(&bCrowd.p, size_t(cap + P) * sizeof(double)));
+    NCU(cudaMalloc(&bCnt.p, size_t(cap + P) * DC_SPLIT * sizeof(int)));
     NCU(cudaMalloc(&bSel.p, size_t(cap) * sizeof(int)));
     NCU(cudaMalloc(&bXl.p, d * sizeof(double)));
     NCU(cudaMalloc(&bXu.p, d * sizeof(double)));
@@ -348,6 +403,19 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
     NCU(cudaMemcpyAsync(bXu.p, h_xu, d * sizeof(double), cudaMemcpyHostToDevice, s));
     NCU(cudaMemcpyAsync(bX[0].p, h_X0, size_t(n_init) * d * sizeof(double), cudaMemcpyHostToDevice, s));
     NCU(cudaMemsetAsync(bEval.p, 0, sizeof(unsigned long long), s));
+    NCU(cudaMalloc(&bLast.p, sizeof(int)));
+    NCHK(set_survival_smem(int(cap + P)));
+
+    // AOED_NSGA2_STAMP=1: CUDA events between the phases of every generation, per-phase totals on stderr (diagnostics)
+    const bool stamp = getenv("AOED_NSGA2_STAMP") != nullptr;
+    std::vector<std::pair<int, cudaEvent_t>> marks;
+    auto mark = [&](int phase) {
+        if (!stamp) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        marks.emplace_back(phase, e);
+    };
 
     auto evaluate = [&](const double* dXc, int64_t rows, double* dF) -> int {
         normalize_kernel<<<unsigned((rows * d + 255) / 256), 256, 0, s>>>(dXc, bXl.as<double>(), bXu.as<double>(), rows, d, bXn.as<double>());
@@ -357,17 +425,17 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
     auto survive = [&](int src, int na, const double* Xb, const double* Fb, const uint8_t* dup, int nb, int keep, int dst) -> int {
         const int n = na + nb;
         merge_kernel<<<(n + 255) / 256, 256, 0, s>>>(bF[src].as<double>(), na, Fb, dup, nb, m, bYT.as<double>());
-        NCHK(launch_rank(m, bYT.as<double>(), n, bRank.as<int>(), s));
-        int np2 = 1;
-        while (np2 < n) np2 <<= 1;
-        SurviveArgs sa;
-        sa.YT = bYT.as<double>(); sa.rank = bRank.as<int>(); sa.crowd = bCrowd.as<double>(); sa.sel = bSel.as<int>();
-        sa.n = n; sa.m = m; sa.keep = keep;
-        const size_t sm = (size_t(np2) + 2 * size_t(n)) * sizeof(int);
-        survive_kernel<<<1, NS_SORT_THREADS, sm, s>>>(sa);
-        gather_kernel<<<(keep + 127) / 128, 128, 0, s>>>(bX[src].as<double>(), bF[src].as<double>(), na, Xb, Fb, bRank.as<int>(),
-                                                          bCrowd.as<double>(), bSel.as<int>(), keep, d, m, bX[dst].as<double>(),
-                                                          bF[dst].as<double>(), bR[dst].as<int>(), bC[dst].as<double>());
+        NCHK(launch_rank(m, bYT.as<double>(), n, bRank.as<int>(), bCnt.as<int>(), keep, bLast.as<int>(), s));
+        mark(4);
+        crowd_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n), s>>>(bYT.as<double>(), bRank.as<int>(), bLast.as<int>(), n, m, bCrowd.as<double>());
+        mark(5);
+        SelectArgs sa;
+        sa.rank = bRank.as<int>(); sa.crowd = bCrowd.as<double>(); sa.last_rank = bLast.as<int>();
+        sa.Xpop = bX[src].as<double>(); sa.Fpop = bF[src].as<double>(); sa.Xoff = Xb; sa.Foff = Fb;
+        sa.n = n; sa.n_cur = na; sa.keep = keep; sa.d = d; sa.m = m; sa.sel = bSel.as<int>();
+        sa.Xnew = bX[dst].as<double>(); sa.Fnew = bF[dst].as<double>(); sa.cnew = bC[dst].as<double>(); sa.rnew = bR[dst].as<int>();
+        select_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n), s>>>(sa);
+        mark(6);
         NCU(cudaGetLastError());
         return AOED_OK;
     };
@@ -383,10 +451,14 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
         va.X = bX[cur].as<double>(); va.rank = bR[cur].as<int>(); va.crowd = bC[cur].as<double>();
         va.xl = bXl.as<double>(); va.xu = bXu.as<double>(); va.Xoff = bXoff.as<double>();
         va.n_cur = n_cur; va.P = P; va.d = d; va.seed = seed; va.gen = g; va.pc = 0.9; va.eta_c = 15.0; va.eta_m = 20.0;
-        variation_kernel<<<((P + 1) / 2 + 127) / 128, 128, 0, s>>>(va);
-        duplicate_kernel<<<(P + 127) / 128, 128, 0, s>>>(bX[cur].as<double>(), n_cur, bXoff.as<double>(), P, d, bDup.as<uint8_t>());
-        count_valid_kernel<<<1, 256, 0, s>>>(bDup.as<uint8_t>(), P, bEval.as<unsigned long long>());
+        mark(0);
+        variation_kernel<<<((P + 1) / 2 * d + 127) / 128, 128, 0, s>>>(va);
+        mark(1);
+        duplicate_kernel<<<(P + DUP_WARPS - 1) / DUP_WARPS, 32 * DUP_WARPS, size_t(n_cur + P) * sizeof(double), s>>>(
+            bX[cur].as<double>(), n_cur, bXoff.as<double>(), P, d, bDup.as<uint8_t>(), bEval.as<unsigned long long>());
+        mark(2);
         NCHK(evaluate(bXoff.as<double>(), P, bFoff.as<double>()));
+        mark(3);
         NCHK(survive(cur, n_cur, bXoff.as<double>(), bFoff.as<double>(), bDup.as<uint8_t>(), P, P, cur ^ 1));
         cur ^= 1;
         n_cur = P;
@@ -396,12 +468,57 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
     unsigned long long off_evals = 0;
     NCU(cudaMemcpyAsync(&off_evals, bEval.p, sizeof(off_evals), cudaMemcpyDeviceToHost, s));
     NCU(cudaStreamSynchronize(s));
+    if (stamp) {
+        static const char* names[8] = {"", "variation", "duplicates", "evaluate", "merge+rank", "crowding", "select", ""};
+        double tot[8] = {0};
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0.f;
+            if (marks[i].first > 0 && cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second) == cudaSuccess)
+                tot[marks[i].first] += ms;
+        }
+        for (int ph = 1; ph < 7; ++ph) fprintf(stderr, "[nsga2 stamp] %-10s %8.1f us/generation\n", names[ph], tot[ph] * 1e3 / std::max(1, n_gen - 1));
+        for (auto& mk : marks) cudaEventDestroy(mk.second);
+    }
     *h_n_out = n_cur;
     if (h_n_eval) *h_n_eval = evals + int64_t(off_evals);
     return AOED_OK;
 }
 
 }  // namespace
+
+extern "C" int aoed_nsga2_survival(int device, int64_t n64, int n_obj, const double* h_F, int64_t keep64, int32_t* h_rank,
+                                   double* h_crowd, int32_t* h_sel) {
+    if (n64 < 1 || keep64 < 1 || keep64 > n64 || n_obj < 1 || !h_F || !h_rank || !h_crowd || !h_sel)
+        return nfail(AOED_ERR_INVALID, "bad argument");
+    if (n64 > RS_MAX_N || n_obj > 8 || rank_small_smem(n_obj, int(n64)) > 200 * 1024)
+        return nfail(AOED_ERR_UNSUPPORTED, "at most 4096 individuals and 8 objectives");
+    const int n = int(n64), m = n_obj, keep = int(keep64);
+    DeviceGuard guard_(device);
+    NCU(guard_.err);
+    std::vector<double> yt(size_t(n) * m);
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < m; ++k) yt[size_t(k) * n + i] = h_F[size_t(i) * m + k];
+    NBuf bYT, bRank, bCnt, bLast, bCrowd, bSel;
+    NCU(cudaMalloc(&bYT.p, yt.size() * sizeof(double)));
+    NCU(cudaMalloc(&bRank.p, size_t(n) * sizeof(int)));
+    NCU(cudaMalloc(&bCnt.p, size_t(n) * DC_SPLIT * sizeof(int)));
+    NCU(cudaMalloc(&bLast.p, sizeof(int)));
+    NCU(cudaMalloc(&bCrowd.p, size_t(n) * sizeof(double)));
+    NCU(cudaMalloc(&bSel.p, size_t(keep) * sizeof(int)));
+    NCU(cudaMemcpy(bYT.p, yt.data(), yt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    NCHK(launch_rank(m, bYT.as<double>(), n, bRank.as<int>(), bCnt.as<int>(), keep, bLast.as<int>(), nullptr));
+    NCHK(set_survival_smem(n));
+    crowd_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n)>>>(bYT.as<double>(), bRank.as<int>(), bLast.as<int>(), n, m, bCrowd.as<double>());
+    SelectArgs sa{};
+    sa.rank = bRank.as<int>(); sa.crowd = bCrowd.as<double>(); sa.last_rank = bLast.as<int>();
+    sa.n = n; sa.n_cur = n; sa.keep = keep; sa.d = 0; sa.m = m; sa.sel = bSel.as<int>();
+    select_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n)>>>(sa);
+    NCU(cudaGetLastError());
+    NCU(cudaMemcpy(h_rank, bRank.p, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost));
+    NCU(cudaMemcpy(h_crowd, bCrowd.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+    NCU(cudaMemcpy(h_sel, bSel.p, size_t(keep) * sizeof(int), cudaMemcpyDeviceToHost));
+    return AOED_OK;
+}
 
 extern "C" int aoed_nsga2_run(aoed_gp_t* gp, int device, int n_var, int n_obj, int acq_kind, const double* h_acq_param,
                               int64_t n_init, const double* h_X0, const double* h_xl, const double* h_xu, int pop_size,

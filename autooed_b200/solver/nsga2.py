@@ -172,6 +172,17 @@ def device_nsga2(acquisition, X0, xl, xu, pop_size, n_gen, seed):
     return Xo[:n_out.value], Fo[:n_out.value], n_eval.value
 
 
+def device_survival(F, keep, device=0):
+    """One rank-and-crowding survival step on the GPU (`aoed_nsga2_survival`): (rank, crowding distance, survivor indices);
+    ranks / distances are only meaningful up to the front that fills `keep` (see the header)."""
+    from autooed_b200 import _lib
+    F = _lib.as_f64(np.atleast_2d(F))
+    n = F.shape[0]
+    rank, crowd, sel = np.empty(n, dtype=np.int32), np.empty(n), np.empty(keep, dtype=np.int32)
+    _lib.check(_lib.load().aoed_nsga2_survival(device, n, F.shape[1], _lib.ptr(F), keep, _lib.ptr(rank), _lib.ptr(crowd), _lib.ptr(sel)))
+    return rank, crowd, sel
+
+
 class NSGA2(Solver):
     '''
     Solver based on NSGA-II.

@@ -137,6 +137,14 @@ int aoed_nsga2_run_rff(int device, int n_var, int n_obj, int n_feat, const doubl
                        const double* h_X0, const double* h_xl, const double* h_xu, int pop_size, int n_gen, uint64_t seed,
                        double* h_X, double* h_F, int64_t* h_n_out, int64_t* h_n_eval);
 
+/* one rank-and-crowding survival step of that loop on its own (pymoo 0.4.1 RankAndCrowdingSurvival, which the reference's
+ * NSGA2 solver runs every generation — autooed/mobo/solver/nsga2.py:17-30): from the objective rows h_F (n x n_obj) keeps
+ * the `keep` best.  Outputs: h_rank (n) front number, fronts are only peeled until `keep` individuals are ranked and every
+ * individual beyond gets (last peeled front + 1); h_crowd (n) crowding distance inside the own front (0 for the unpeeled
+ * rest); h_sel (keep) indices of the survivors ordered by (rank, crowding distance descending, index).  n <= 4096. */
+int aoed_nsga2_survival(int device, int64_t n, int n_obj, const double* h_F, int64_t keep, int32_t* h_rank, double* h_crowd,
+                        int32_t* h_sel);
+
 /* ---- Thompson-sampling acquisition -----------------------------------------------
  * replaces ThompsonSampling._evaluate (autooed/mobo/acquisition/ts.py:65-87) incl. its un-normalisation: value, gradient
  * and Hessian of the random-Fourier-feature posterior sample  f_o(x) = factor_o * sum_j theta_oj cos(W_oj . x + b_oj).

@@ -96,3 +96,42 @@ def test_first_generation_only_and_fallbacks():
     sc = NSGA2(cprob, n_gen=3, pop_size=20)
     Xc2, _ = sc.solve(X, Y, 4, acq)  # constraints are evaluated by the real problem on the host: host loop
     assert Xc2.shape == (20, 6) and not sc._device_eligible(44)
+
+
+@pytest.mark.parametrize("n,m,keep,decimals,shift", [(400, 2, 200, 3, 0.0), (2000, 2, 1000, 6, 1.0), (2000, 2, 900, 6, 1.0),
+                                                     (2000, 3, 1000, 2, 0.0), (1300, 4, 1000, 1, 0.0), (64, 1, 10, 6, 0.0),
+                                                     (4096, 2, 2048, 3, 0.0), (4096, 3, 2000, 6, 1.0), (50, 2, 50, 2, 0.0)])
+def test_survival_step_matches_host(n, m, keep, decimals, shift):
+    """`aoed_nsga2_survival` (the rank / crowding / selection kernels of the device loop) against the host NSGA-II's
+    rank-and-crowding survival — bit-exact: same survivors in the same order, same crowding distances.  Rounded
+    objectives give ties and duplicate rows; a partly converged population gives one huge first front."""
+    from autooed_b200.solver.nsga2 import NSGA2Algorithm, device_survival
+    rng = np.random.default_rng(n * 10 + m)
+    F = np.round(rng.random((n, m)), decimals)
+    if m >= 2:  # half of the rows on a common trade-off curve: mutually non-dominated
+        t = rng.random(n // 2)
+        F[: n // 2, 0], F[: n // 2, 1] = t, 1.0 - t
+        F[: n // 2, 2:] = 0.5
+        F[n // 2:] += shift  # shift = 1: nothing dominates the curve, the first front alone has n / 2 members
+    F[5] = F[3]
+    rank, crowd, sel = device_survival(F, keep)
+    algo = NSGA2Algorithm(pop_size=keep, rank_fn=lambda G: _peel(G))
+    h_rank, h_crowd = algo._rank_and_crowding(F)
+    order = np.lexsort((np.arange(n), -h_crowd, h_rank))[:keep]
+    last = h_rank[order].max()
+    peeled = h_rank <= last
+    assert np.array_equal(rank[peeled], h_rank[peeled]) and (rank[~peeled] == last + 1).all()
+    assert np.array_equal(crowd[peeled], h_crowd[peeled])
+    assert np.array_equal(sel, order)
+
+
+def _peel(Y):
+    n = len(Y)
+    dom = (Y[:, None, :] <= Y[None, :, :]).all(-1) & (Y[:, None, :] < Y[None, :, :]).any(-1)
+    cnt, want, r = dom.sum(0), np.full(n, -1), 0
+    while (want < 0).any():
+        front = (want < 0) & (cnt == 0)
+        want[front] = r
+        cnt = cnt - dom[front].sum(0)
+        r += 1
+    return want
