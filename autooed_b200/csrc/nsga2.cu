@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <climits>
@@ -177,110 +178,48 @@ __global__ void merge_kernel(const double* __restrict__ Fpop, int n_cur, const d
     }
 }
 
-// ---- crowding distance + survival by pairwise counting (no sort, many CTAs) ---------------------------------
-// A warp owns 32 consecutive individuals, the 8 warps of a CTA split the individuals they are compared with, which are
+// ---- crowding distance + survival by pairwise counting (no sort loop, many CTAs) ----------------------------
+// A warp owns 32 consecutive individuals, the warps of a CTA split the individuals they are compared with, which are
 // staged in shared memory first (see dom_count_kernel).  Individuals ranked above *last_rank (the unpeeled rest of an
-// early-stopped sort) can never survive and are skipped.
+// early-stopped sort) can never survive and are skipped ("relevant" = rank <= *last_rank).
 constexpr int CW_WARPS = 16;
 inline size_t crowd_smem(int n) { return size_t(n) * (sizeof(double) + 2 * sizeof(int)); }
 
-// crowding distance: for every objective the neighbours of i inside its own front in (value, index) order — the
-// order a stable sort gives (pymoo calc_crowding_distance); front boundary -> +inf.  Only the neighbours' VALUES enter
-// the distance, so the scan keeps branch-free running max / min of the values before / after i and counts them.
-__global__ void __launch_bounds__(32 * CW_WARPS) crowd_kernel(const double* __restrict__ YT, const int* __restrict__ rank,
-                                                              const int* __restrict__ last_rank, int n, int m,
-                                                              double* __restrict__ crowd) {
-    extern __shared__ double cw_smem[];
-    double* fs = cw_smem;                           // [nr] objective k of the relevant individuals (rank <= *last_rank)
-    int* rs = reinterpret_cast<int*>(fs + n);       // [nr] their ranks
-    int* js = rs + n;                               // [nr] their indices (any order: the scan only takes max / min / counts)
-    __shared__ double s_pf[CW_WARPS][32], s_nf[CW_WARPS][32], s_lo[CW_WARPS][32], s_hi[CW_WARPS][32];
-    __shared__ int s_np[CW_WARPS][32], s_nn[CW_WARPS][32];
-    __shared__ int n_rel;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = blockIdx.x * 32 + lane;
-    const int last = *last_rank;
-    const int ri = i < n ? rank[i] : INT_MAX;
-    const bool active = i < n && ri <= last;
-    if (threadIdx.x == 0) n_rel = 0;
-    if (__syncthreads_or(active) == 0) {
-        if (w == 0 && i < n) crowd[i] = 0.0;
-        return;
-    }
-    for (int j = threadIdx.x; j < n; j += 32 * CW_WARPS) {
-        const int r = rank[j];
+struct SurvivalTables {
+    const double* YT;     // [m][n] merged objectives
+    const int* rank;      // [n]
+    const int* last_rank;
+    int* order;           // [m][n] order[k][t] = individual at position t when sorted by (rank, objective k, index)
+    int* pos;             // [m][n] inverse of order (relevant individuals only)
+    int* gbase;           // [n] first position of i's front
+    int* gsize;           // [n] size of i's front
+    int n, m;
+};
+
+// compacts the relevant individuals into shared memory: rs = rank, js = index; returns how many
+__device__ int stage_relevant(const int* __restrict__ rank, int n, int last, int* rs, int* js, int* n_rel) {
+    for (int j0 = 0; j0 < n; j0 += 32 * CW_WARPS) {
+        const int j = j0 + threadIdx.x;
+        const int r = j < n ? rank[j] : INT_MAX;
+        const int q = warp_slot(n_rel, r <= last);
         if (r <= last) {
-            const int q = atomicAdd(&n_rel, 1);
             rs[q] = r;
             js[q] = j;
         }
     }
     __syncthreads();
-    const int nr = n_rel;
-    double acc = 0.0;
-    for (int k = 0; k < m; ++k) {
-        const double* f = YT + int64_t(k) * n;
-        for (int q = threadIdx.x; q < nr; q += 32 * CW_WARPS) fs[q] = f[js[q]];
-        __syncthreads();
-        const double fi = active ? f[i] : 0.0;
-        double pf = -INFINITY, nf = INFINITY, lo = INFINITY, hi = -INFINITY;
-        int n_before = 0, n_after = 0;  // members of i's front before / after it in (f, index) order
-        if (active) {
-#pragma unroll 4
-            for (int q = w; q < nr; q += CW_WARPS) {
-                const bool mine = rs[q] == ri;
-                const double fj = fs[q];
-                const int j = js[q];
-                const bool before = mine && (fj < fi || (fj == fi && j < i));
-                const bool after = mine && (fj > fi || (fj == fi && j > i));
-                lo = fmin(lo, mine ? fj : INFINITY);
-                hi = fmax(hi, mine ? fj : -INFINITY);
-                pf = fmax(pf, before ? fj : -INFINITY);
-                nf = fmin(nf, after ? fj : INFINITY);
-                n_before += before ? 1 : 0;
-                n_after += after ? 1 : 0;
-            }
-        }
-        s_pf[w][lane] = pf; s_nf[w][lane] = nf; s_lo[w][lane] = lo; s_hi[w][lane] = hi;
-        s_np[w][lane] = n_before; s_nn[w][lane] = n_after;
-        __syncthreads();
-        if (w == 0 && active) {
-            for (int q = 1; q < CW_WARPS; ++q) {
-                pf = fmax(pf, s_pf[q][lane]);
-                nf = fmin(nf, s_nf[q][lane]);
-                lo = fmin(lo, s_lo[q][lane]);
-                hi = fmax(hi, s_hi[q][lane]);
-                n_before += s_np[q][lane];
-                n_after += s_nn[q][lane];
-            }
-            const double span = hi - lo;
-            if (n_before == 0 || n_after == 0) acc = INFINITY;
-            else if (span > 0.0 && span < DBL_MAX) acc += (nf - pf) / span;
-        }
-        __syncthreads();
-    }
-    if (w == 0 && i < n) crowd[i] = active ? acc : 0.0;
+    return *n_rel;
 }
 
-// survivors: position of i in the order (rank, crowding distance descending, index) = number of individuals before it;
-// the individuals whose position is below `keep` are copied to that row of the next population
-struct SelectArgs {
-    const int* rank;         // [n] merged table
-    const double* crowd;     // [n]
-    const int* last_rank;
-    const double *Xpop, *Fpop, *Xoff, *Foff;  // merged table = population rows [0, n_cur) then offspring rows
-    int n, n_cur, keep, d, m;
-    int* sel;                // [keep] survivors' indices in the merged table, best first
-    double *Xnew, *Fnew, *cnew;
-    int* rnew;
-};
-
-__global__ void __launch_bounds__(32 * CW_WARPS) select_kernel(SelectArgs p) {
+// positions by counting: for every objective, where individual i stands when its front is ordered by (value, index) —
+// the order a stable sort gives.  ~10 instructions per pair; the neighbour lookups happen in select_kernel.
+__global__ void __launch_bounds__(32 * CW_WARPS) crowd_pos_kernel(SurvivalTables p) {
     extern __shared__ double cw_smem[];
     const int n = p.n;
-    double* cs = cw_smem;                      // [nr] crowding distances of the relevant individuals
-    int* rs = reinterpret_cast<int*>(cs + n);  // [nr] ranks
+    double* fs = cw_smem;                      // [nr] objective k of the relevant individuals
+    int* rs = reinterpret_cast<int*>(fs + n);  // [nr] ranks
     int* js = rs + n;                          // [nr] indices
-    __shared__ int part[32];
+    __shared__ int c_pos[32], c_base[32], c_size[32];
     __shared__ int n_rel;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = blockIdx.x * 32 + lane;
     const int last = *p.last_rank;
@@ -288,19 +227,99 @@ __global__ void __launch_bounds__(32 * CW_WARPS) select_kernel(SelectArgs p) {
     const bool active = i < n && ri <= last;
     if (threadIdx.x == 0) n_rel = 0;
     if (__syncthreads_or(active) == 0) return;
-    for (int j = threadIdx.x; j < n; j += 32 * CW_WARPS) {
-        const int r = p.rank[j];
-        if (r <= last) {
-            const int q = atomicAdd(&n_rel, 1);
-            rs[q] = r;
-            js[q] = j;
-            cs[q] = p.crowd[j];
+    const int nr = stage_relevant(p.rank, n, last, rs, js, &n_rel);
+    int base = 0;
+    for (int k = 0; k < p.m; ++k) {
+        const double* f = p.YT + int64_t(k) * n;
+        for (int q = threadIdx.x; q < nr; q += 32 * CW_WARPS) fs[q] = f[js[q]];
+        if (w == 0) c_pos[lane] = c_base[lane] = c_size[lane] = 0;
+        __syncthreads();
+        if (active) {
+            const double fi = f[i];
+            int c = 0, cb = 0, cs = 0;
+#pragma unroll 4
+            for (int q = w; q < nr; q += CW_WARPS) {
+                const int rj = rs[q];
+                const double fj = fs[q];
+                const bool mine = rj == ri;
+                c += (mine && (fj < fi || (fj == fi && js[q] < i))) ? 1 : 0;
+                cb += rj < ri ? 1 : 0;
+                cs += mine ? 1 : 0;
+            }
+            atomicAdd(&c_pos[lane], c);
+            if (k == 0) {
+                atomicAdd(&c_base[lane], cb);
+                atomicAdd(&c_size[lane], cs);
+            }
+        }
+        __syncthreads();
+        if (w == 0 && active) {
+            if (k == 0) {
+                base = c_base[lane];
+                p.gbase[i] = base;
+                p.gsize[i] = c_size[lane];
+            }
+            const int t = base + c_pos[lane];
+            p.pos[int64_t(k) * n + i] = t;
+            p.order[int64_t(k) * n + t] = i;
+        }
+        __syncthreads();
+    }
+}
+
+// crowding distance of a relevant individual from the position tables (pymoo calc_crowding_distance: neighbours in its
+// own front per objective, normalised by the front's extent; front boundary -> +inf)
+__device__ __forceinline__ double crowding_of(const SurvivalTables& p, int i) {
+    const int b = p.gbase[i], e = b + p.gsize[i] - 1;
+    double acc = 0.0;
+    for (int k = 0; k < p.m; ++k) {
+        const int* o = p.order + int64_t(k) * p.n;
+        const double* f = p.YT + int64_t(k) * p.n;
+        const int t = p.pos[int64_t(k) * p.n + i];
+        if (t == b || t == e) {
+            acc = INFINITY;
+        } else {
+            const double span = f[o[e]] - f[o[b]];
+            if (span > 0.0 && span < DBL_MAX) acc += (f[o[t + 1]] - f[o[t - 1]]) / span;
         }
     }
+    return acc;
+}
+
+// survivors: position of i in the order (rank, crowding distance descending, index) = number of individuals before it;
+// the individuals whose position is below `keep` are copied to that row of the next population
+struct SelectArgs {
+    SurvivalTables tab;
+    double* crowd;           // [n] out: crowding distance (0 for the irrelevant rest)
+    const double *Xpop, *Fpop, *Xoff, *Foff;  // merged table = population rows [0, n_cur) then offspring rows
+    int n_cur, keep, d;
+    int* sel;                // [keep] survivors' indices in the merged table, best first
+    double *Xnew, *Fnew, *cnew;
+    int* rnew;
+};
+
+__global__ void __launch_bounds__(32 * CW_WARPS) select_kernel(SelectArgs p) {
+    extern __shared__ double cw_smem[];
+    const int n = p.tab.n;
+    double* cs = cw_smem;                      // [nr] crowding distances of the relevant individuals
+    int* rs = reinterpret_cast<int*>(cs + n);  // [nr] ranks
+    int* js = rs + n;                          // [nr] indices
+    __shared__ int part[32];
+    __shared__ int n_rel;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = blockIdx.x * 32 + lane;
+    const int last = *p.tab.last_rank;
+    const int ri = i < n ? p.tab.rank[i] : INT_MAX;
+    const bool active = i < n && ri <= last;
+    if (threadIdx.x == 0) n_rel = 0;
     if (w == 0) part[lane] = 0;
+    if (__syncthreads_or(active) == 0) {
+        if (w == 0 && i < n) p.crowd[i] = 0.0;
+        return;
+    }
+    const int nr = stage_relevant(p.tab.rank, n, last, rs, js, &n_rel);
+    for (int q = threadIdx.x; q < nr; q += 32 * CW_WARPS) cs[q] = crowding_of(p.tab, js[q]);
     __syncthreads();
-    const int nr = n_rel;
-    const double ci = active ? p.crowd[i] : 0.0;
+    const double ci = active ? crowding_of(p.tab, i) : 0.0;
     if (active) {
         int c = 0;
 #pragma unroll 4
@@ -312,14 +331,16 @@ __global__ void __launch_bounds__(32 * CW_WARPS) select_kernel(SelectArgs p) {
         atomicAdd(&part[lane], c);
     }
     __syncthreads();
+    if (w == 0 && i < n) p.crowd[i] = ci;
     if (w == 0 && active && part[lane] < p.keep) {
         const int t = part[lane];
         p.sel[t] = i;
         if (p.Xnew) {
+            const int m = p.tab.m;
             const double* x = i < p.n_cur ? p.Xpop + int64_t(i) * p.d : p.Xoff + int64_t(i - p.n_cur) * p.d;
-            const double* f = i < p.n_cur ? p.Fpop + int64_t(i) * p.m : p.Foff + int64_t(i - p.n_cur) * p.m;
+            const double* f = i < p.n_cur ? p.Fpop + int64_t(i) * m : p.Foff + int64_t(i - p.n_cur) * m;
             for (int k = 0; k < p.d; ++k) p.Xnew[int64_t(t) * p.d + k] = x[k];
-            for (int k = 0; k < p.m; ++k) p.Fnew[int64_t(t) * p.m + k] = f[k];
+            for (int k = 0; k < m; ++k) p.Fnew[int64_t(t) * m + k] = f[k];
             p.rnew[t] = ri;
             p.cnew[t] = ci;
         }
@@ -333,6 +354,24 @@ struct NBuf {
     }
     template <typename T>
     T* as() { return static_cast<T*>(p); }
+};
+
+// the scratch tables of one survival step for up to n individuals and m objectives
+struct SurvivalScratch {
+    NBuf order, pos, gbase, gsize;
+    int alloc(int n, int m) {
+        NCU(cudaMalloc(&order.p, size_t(n) * m * sizeof(int)));
+        NCU(cudaMalloc(&pos.p, size_t(n) * m * sizeof(int)));
+        NCU(cudaMalloc(&gbase.p, size_t(n) * sizeof(int)));
+        NCU(cudaMalloc(&gsize.p, size_t(n) * sizeof(int)));
+        return AOED_OK;
+    }
+    SurvivalTables tables(const double* YT, const int* rank, const int* last_rank, int n, int m) {
+        SurvivalTables t;
+        t.YT = YT; t.rank = rank; t.last_rank = last_rank; t.n = n; t.m = m;
+        t.order = order.as<int>(); t.pos = pos.as<int>(); t.gbase = gbase.as<int>(); t.gsize = gsize.as<int>();
+        return t;
+    }
 };
 
 int launch_rank(int m, const double* YT, int n, int32_t* rank, int* cnt_scratch, int need, int* last_rank, cudaStream_t s) {
@@ -354,7 +393,7 @@ namespace {
 
 // opt-in to the shared memory the staging kernels need for n individuals (above the 48 KB default from n ~ 4000)
 int set_survival_smem(int n) {
-    NCU(cudaFuncSetAttribute(crowd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(crowd_smem(n))));
+    NCU(cudaFuncSetAttribute(crowd_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(crowd_smem(n))));
     NCU(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(crowd_smem(n))));
     return AOED_OK;
 }
@@ -405,6 +444,8 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
     NCU(cudaMemsetAsync(bEval.p, 0, sizeof(unsigned long long), s));
     NCU(cudaMalloc(&bLast.p, sizeof(int)));
     NCHK(set_survival_smem(int(cap + P)));
+    SurvivalScratch scratch;
+    NCHK(scratch.alloc(int(cap + P), m));
 
     // AOED_NSGA2_STAMP=1: CUDA events between the phases of every generation, per-phase totals on stderr (diagnostics)
     const bool stamp = getenv("AOED_NSGA2_STAMP") != nullptr;
@@ -427,12 +468,13 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
         merge_kernel<<<(n + 255) / 256, 256, 0, s>>>(bF[src].as<double>(), na, Fb, dup, nb, m, bYT.as<double>());
         NCHK(launch_rank(m, bYT.as<double>(), n, bRank.as<int>(), bCnt.as<int>(), keep, bLast.as<int>(), s));
         mark(4);
-        crowd_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n), s>>>(bYT.as<double>(), bRank.as<int>(), bLast.as<int>(), n, m, bCrowd.as<double>());
-        mark(5);
         SelectArgs sa;
-        sa.rank = bRank.as<int>(); sa.crowd = bCrowd.as<double>(); sa.last_rank = bLast.as<int>();
+        sa.tab = scratch.tables(bYT.as<double>(), bRank.as<int>(), bLast.as<int>(), n, m);
+        crowd_pos_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n), s>>>(sa.tab);
+        mark(5);
+        sa.crowd = bCrowd.as<double>();
         sa.Xpop = bX[src].as<double>(); sa.Fpop = bF[src].as<double>(); sa.Xoff = Xb; sa.Foff = Fb;
-        sa.n = n; sa.n_cur = na; sa.keep = keep; sa.d = d; sa.m = m; sa.sel = bSel.as<int>();
+        sa.n_cur = na; sa.keep = keep; sa.d = d; sa.sel = bSel.as<int>();
         sa.Xnew = bX[dst].as<double>(); sa.Fnew = bF[dst].as<double>(); sa.cnew = bC[dst].as<double>(); sa.rnew = bR[dst].as<int>();
         select_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n), s>>>(sa);
         mark(6);
@@ -446,6 +488,7 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
     NCHK(survive(0, int(n_init), nullptr, nullptr, nullptr, 0, n_cur, 1));
     int cur = 1;
     int64_t evals = n_init;
+    const auto t_loop = std::chrono::steady_clock::now();
     for (int g = 1; g < n_gen; ++g) {
         VarArgs va;
         va.X = bX[cur].as<double>(); va.rank = bR[cur].as<int>(); va.crowd = bC[cur].as<double>();
@@ -463,12 +506,16 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
         cur ^= 1;
         n_cur = P;
     }
+    const auto t_enqueued = std::chrono::steady_clock::now();
     NCU(cudaMemcpyAsync(h_X, bX[cur].p, size_t(n_cur) * d * sizeof(double), cudaMemcpyDeviceToHost, s));
     NCU(cudaMemcpyAsync(h_F, bF[cur].p, size_t(n_cur) * m * sizeof(double), cudaMemcpyDeviceToHost, s));
     unsigned long long off_evals = 0;
     NCU(cudaMemcpyAsync(&off_evals, bEval.p, sizeof(off_evals), cudaMemcpyDeviceToHost, s));
     NCU(cudaStreamSynchronize(s));
     if (stamp) {
+        fprintf(stderr, "[nsga2 stamp] host enqueue %8.1f us/generation, until drained %8.1f us/generation\n",
+                std::chrono::duration<double, std::micro>(t_enqueued - t_loop).count() / std::max(1, n_gen - 1),
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_loop).count() / std::max(1, n_gen - 1));
         static const char* names[8] = {"", "variation", "duplicates", "evaluate", "merge+rank", "crowding", "select", ""};
         double tot[8] = {0};
         for (size_t i = 1; i < marks.size(); ++i) {
@@ -508,10 +555,13 @@ extern "C" int aoed_nsga2_survival(int device, int64_t n64, int n_obj, const dou
     NCU(cudaMemcpy(bYT.p, yt.data(), yt.size() * sizeof(double), cudaMemcpyHostToDevice));
     NCHK(launch_rank(m, bYT.as<double>(), n, bRank.as<int>(), bCnt.as<int>(), keep, bLast.as<int>(), nullptr));
     NCHK(set_survival_smem(n));
-    crowd_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n)>>>(bYT.as<double>(), bRank.as<int>(), bLast.as<int>(), n, m, bCrowd.as<double>());
+    SurvivalScratch scratch;
+    NCHK(scratch.alloc(n, m));
     SelectArgs sa{};
-    sa.rank = bRank.as<int>(); sa.crowd = bCrowd.as<double>(); sa.last_rank = bLast.as<int>();
-    sa.n = n; sa.n_cur = n; sa.keep = keep; sa.d = 0; sa.m = m; sa.sel = bSel.as<int>();
+    sa.tab = scratch.tables(bYT.as<double>(), bRank.as<int>(), bLast.as<int>(), n, m);
+    crowd_pos_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n)>>>(sa.tab);
+    sa.crowd = bCrowd.as<double>();
+    sa.n_cur = n; sa.keep = keep; sa.d = 0; sa.sel = bSel.as<int>();
     select_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n)>>>(sa);
     NCU(cudaGetLastError());
     NCU(cudaMemcpy(h_rank, bRank.p, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost));

@@ -11,6 +11,18 @@ namespace aoed {
 // domination counts, then front peeling with the counts decremented by the members of each peeled front — no host
 // round trip per front.  Same semantics as the multi-launch path below (rank = front number, pymoo NonDominatedSorting).
 constexpr int RS_THREADS = 1024;
+
+// slot = (*ctr)++ for the lanes with `pred`, one shared-memory atomic per warp instead of one per lane (a thousand
+// same-address atomics serialise).  Must be reached by all 32 lanes; returns -1 for lanes without `pred`.
+__device__ __forceinline__ int warp_slot(int* ctr, bool pred) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return -1;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(ctr, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return pred ? base + __popc(mask & ((1u << lane) - 1u)) : -1;
+}
 constexpr int RS_MAX_N = 4096;
 
 // domination counts of all n points over many CTAs: a warp owns 32 consecutive points; the candidates for "dominates
@@ -103,11 +115,15 @@ __global__ void __launch_bounds__(RS_THREADS) rank_small_kernel(const double* __
     for (int r = 0; n_left > 0; ++r) {
         if (tid == 0) n_front = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += RS_THREADS)
-            if (rk[i] < 0 && cnt[i] == 0) {
+        for (int i0 = 0; i0 < n; i0 += RS_THREADS) {
+            const int i = i0 + tid;
+            const bool in_front = i < n && rk[i] < 0 && cnt[i] == 0;
+            const int slot = warp_slot(&n_front, in_front);
+            if (in_front) {
                 rk[i] = r;
-                front[atomicAdd(&n_front, 1)] = i;
+                front[slot] = i;
             }
+        }
         __syncthreads();
         const int nf = n_front;
         if (nf == 0) break;  // cannot happen for finite inputs (a minimal element always exists); NaN rows stay at -1
@@ -152,18 +168,28 @@ constexpr int RS_SPLIT_N = 1024;  // above this the domination counts come from 
 
 // launches the sort of n <= RS_MAX_N points on stream s; `cnt_scratch` ([DC_SPLIT * n] ints on the device) enables the split
 // counting for large n (pass nullptr to stay with the single kernel)
+constexpr size_t RS_SMEM_LIMIT = 200 * 1024;  // callers check rank_small_smem(m, n) against this
+
 template <int M>
 cudaError_t launch_rank_small_m(const double* YT, int n, int32_t* rank, int* cnt_scratch, int need, cudaStream_t s,
                                 int* last_rank_out = nullptr) {
     const size_t sm = rank_small_smem(M, n);
-    cudaError_t e = cudaFuncSetAttribute(rank_small_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));
+    const int chunk = dom_count_chunk(n);
+    const size_t dsm = size_t(M) * chunk * sizeof(double);
+    static thread_local int opted_in_device = -1;  // the shared-memory opt-in is per device and costs a driver call
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    if (opted_in_device != dev) {
+        e = cudaFuncSetAttribute(rank_small_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(RS_SMEM_LIMIT));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(dom_count_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(size_t(M) * dom_count_chunk(RS_MAX_N) * sizeof(double)));
+        if (e != cudaSuccess) return e;
+        opted_in_device = dev;
+    }
     const int* cnt_in = nullptr;
     if (cnt_scratch && n > RS_SPLIT_N) {
-        const int chunk = dom_count_chunk(n);
-        const size_t dsm = size_t(M) * chunk * sizeof(double);
-        e = cudaFuncSetAttribute(dom_count_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dsm));
-        if (e != cudaSuccess) return e;
         dom_count_kernel<M><<<dim3((n + 31) / 32, DC_SPLIT), 32 * DC_WARPS, dsm, s>>>(YT, n, chunk, cnt_scratch);
         cnt_in = cnt_scratch;
     }

@@ -5,4 +5,4 @@ python tools/profile_nsga2.py identity 200 200 120 > gpurun_out/ns_c1.log 2>&1
 python tools/profile_nsga2.py ei 1000 200 120 > gpurun_out/ns_c2.log 2>&1
 AOED_NSGA2_STAMP=1 python tools/profile_nsga2.py identity 200 200 120 > gpurun_out/ns_c1_stamp.log 2>&1
 AOED_NSGA2_STAMP=1 python tools/profile_nsga2.py ei 1000 200 120 > gpurun_out/ns_c2_stamp.log 2>&1
-tail -1 gpurun_out/ns_c1.log; tail -1 gpurun_out/ns_c2.log; tail -7 gpurun_out/ns_c1_stamp.log | head -6;  tail -7 gpurun_out/ns_c2_stamp.log | head -6
+tail -1 gpurun_out/ns_c1.log; tail -1 gpurun_out/ns_c2.log; tail -8 gpurun_out/ns_c1_stamp.log | head -7;  tail -8 gpurun_out/ns_c2_stamp.log | head -7
