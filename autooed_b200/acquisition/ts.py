@@ -12,14 +12,7 @@ from scipy.stats.distributions import chi2
 from autooed_b200 import _lib
 from autooed_b200.acquisition.base import Acquisition
 from autooed_b200.utils.sampling import lhs
-
-try:  # M x M (M = 100) factorisations: a many-threaded BLAS spends ~80 ms per call spinning on them, one thread 0.3 ms
-    from threadpoolctl import threadpool_limits as _blas_threads
-except ImportError:  # pragma: no cover
-    import contextlib
-
-    def _blas_threads(limits=None):
-        return contextlib.nullcontext()
+from autooed_b200.utils.blas import single_threaded_blas
 
 
 class ThompsonSampling(Acquisition):
@@ -39,7 +32,7 @@ class ThompsonSampling(Acquisition):
         sm = self.surrogate_model
         n_sample, n_var, nu, M = Xn.shape[0], sm.n_var, sm.nu, self.M
         self.thetas, self.Ws, self.bs, self.sf2s = [], [], [], []
-        with _blas_threads(limits=1):
+        with single_threaded_blas():
             self._fit_objectives(sm, Xn, Yn, n_var, nu, M)
 
     def _fit_objectives(self, sm, Xn, Yn, n_var, nu, M):

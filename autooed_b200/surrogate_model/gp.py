@@ -16,14 +16,7 @@ from scipy.optimize import minimize
 
 from autooed_b200 import _lib
 from autooed_b200.surrogate_model.base import SurrogateModel
-
-try:  # the optimiser's own linear algebra is tiny (p = n_var + 2): keep a many-threaded BLAS from spinning on it
-    from threadpoolctl import threadpool_limits as _blas_threads
-except ImportError:  # pragma: no cover
-    import contextlib
-
-    def _blas_threads(limits=None):
-        return contextlib.nullcontext()
+from autooed_b200.utils.blas import single_threaded_blas
 
 
 def initial_theta(n_var):
@@ -242,7 +235,7 @@ class GaussianProcess(SurrogateModel):
                 pool.finish(b)
 
         threads = [threading.Thread(target=worker, args=(b,), daemon=True) for b in range(len(problems))]
-        with _blas_threads(limits=1):
+        with single_threaded_blas():
             for t in threads:
                 t.start()
             pool.serve()
