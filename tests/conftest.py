@@ -16,8 +16,8 @@ def pytest_configure(config):
 
 def golden_files():
     """GP / acquisition fixtures (one per problem shape x nu); pareto_cases.npz is the multi-objective fixture, ts_*.npz
-    the Thompson-sampling ones."""
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("ts_", "pareto_")))
+    the Thompson-sampling ones, async_*.npz the penalised-acquisition ones."""
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("ts_", "pareto_", "async_")))
 
 
 @pytest.fixture(scope="session")
