@@ -18,6 +18,7 @@
 #include "fit_small2.cuh"
 #include "hessian.cuh"
 #include "posterior.cuh"
+#include "small_eval.cuh"
 #include "trmm.cuh"
 #include "trmm_tma.cuh"
 
@@ -492,9 +493,59 @@ struct EvalOut {
     double *F, *S, *dF, *dS, *A, *dA;
 };
 
+template <int NU, int DP>
+void launch_small_eval(const SmallEvalArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+    static thread_local int opted_in_device = -1;  // shared-memory opt-in (up to 105 KB at n_train 256, d 32): once per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (opted_in_device != dev) {
+        cudaFuncSetAttribute(small_eval_kernel<NU, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(small_eval_smem(SE_MAX_NPAD, DP)));
+        opted_in_device = dev;
+    }
+    small_eval_kernel<NU, DP><<<grid, SE_THREADS, smem, s>>>(a);
+}
+
+template <int NU>
+void launch_small_eval_dp(int DP, const SmallEvalArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+    switch (DP) {
+        case 8: launch_small_eval<NU, 8>(a, grid, smem, s); break;
+        case 16: launch_small_eval<NU, 16>(a, grid, smem, s); break;
+        case 24: launch_small_eval<NU, 24>(a, grid, smem, s); break;
+        default: launch_small_eval<NU, 32>(a, grid, smem, s); break;
+    }
+}
+
+// value-only calls on small batches and small training sets: one fused kernel (small_eval.cuh).
+// AOED_SMALL_EVAL=0 sends them down the chunked path instead (tests compare the two).
+bool small_eval_applies(const aoed_gp* gp, int64_t rows, bool want_grad) {
+    if (want_grad || gp->Npad > SE_MAX_NPAD || rows > SE_MAX_ROWS) return false;
+    const char* env = getenv("AOED_SMALL_EVAL");
+    return !(env && env[0] == '0');
+}
+
+int eval_small(aoed_gp* gp, const double* d_X, int64_t rows, bool want_std, const AcqDev& acq, const EvalOut& out, cudaStream_t s) {
+    SmallEvalArgs a;
+    a.X = d_X; a.Ts = gp->dTs; a.alpha = gp->dAlpha; a.ell = gp->dEll; a.model = gp->dModel; a.LinvT = gp->dLinvT;
+    a.N = gp->N; a.Npad = gp->Npad; a.d = gp->d; a.m = gp->m; a.std = want_std ? 1 : 0; a.rows = rows; a.acq = acq;
+    a.F = out.F; a.S = out.S; a.A = out.A;
+    const dim3 grid(unsigned((rows + SE_TC - 1) / SE_TC), gp->m);
+    const size_t smem = small_eval_smem(gp->Npad, gp->DP);
+    switch (gp->nu) {
+        case 1: launch_small_eval_dp<1>(gp->DP, a, grid, smem, s); break;
+        case 3: launch_small_eval_dp<3>(gp->DP, a, grid, smem, s); break;
+        case 5: launch_small_eval_dp<5>(gp->DP, a, grid, smem, s); break;
+        default: launch_small_eval_dp<-1>(gp->DP, a, grid, smem, s); break;
+    }
+    gp->n_launches++;
+    CU(cudaGetLastError());
+    return AOED_OK;
+}
+
 // One chunk of `rows` candidates (rows <= ws.cols), device-resident, row-major input d_X[rows][d].
 int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool want_std, bool want_grad,
                const AcqDev& acq, const EvalOut& out, cudaStream_t s) {
+    if (small_eval_applies(gp, rows, want_grad)) return eval_small(gp, d_X, rows, want_std, acq, out, s);
     const int m = gp->m, DP = gp->DP, Npad = gp->Npad;
     const int ldc = int(w.cols);
     const int colTiles = int((rows + 127) / 128);

@@ -66,7 +66,9 @@ def test_mean_and_gradient_vs_reference(name):
     tol = cond_tol(g)
     assert rel(out["F"], g["mean_F"]) < tol
     assert rel(out["dF"], g["mean_dF"]) < tol
-    assert np.array_equal(gp.predict(g["Xs"]), out["F"])
+    # a value-only call of this size runs in the fused small-batch kernel: same mean up to the summation order of
+    # sum_j k_j alpha_j, whose cancellation grows with cond(K) like the tolerance against the reference does
+    assert rel(gp.predict(g["Xs"]), out["F"]) < 1e-2 * tol
 
 
 @pytest.mark.parametrize("name", FILES)
@@ -111,7 +113,7 @@ def test_std_gradient_rowstack_vs_reference(name):
 
 @pytest.mark.parametrize("name", FILES)
 @pytest.mark.parametrize("kind", ["identity", "ucb", "ei", "pi"])
-def test_acquisition_fused(name, kind):
+def test_acquisition_fused(name, kind, monkeypatch):
     import autooed_b200 as ab
     g = load(name)
     gp = build(g)
@@ -130,7 +132,15 @@ def test_acquisition_fused(name, kind):
     # value-only batched call vs the reference (what NSGA-II issues every generation)
     Fb, dFb, _ = acq.evaluate(g["Xs"])
     assert dFb is None
-    assert np.allclose(Fb, F, rtol=0, atol=0)
+    # ... on the chunked path the value does not depend on which derivatives were requested ...
+    monkeypatch.setenv("AOED_SMALL_EVAL", "0")
+    assert np.array_equal(acq.evaluate(g["Xs"])[0], F)
+    monkeypatch.delenv("AOED_SMALL_EVAL")
+    # ... and the fused small-batch kernel, which serves a call of this size, differs by the summation order only:
+    # compared where sigma is not cancellation noise (the acquisitions divide by it)
+    prior_all = np.exp(g["theta"][:, 0]) + np.exp(g["theta"][:, -1])
+    solid = (((val["S"] / g["y_scale"]) ** 2 / prior_all) > 1e-6).all(axis=1)
+    assert np.allclose(Fb[solid], F[solid], rtol=max(1e-9, 1e-2 * cond_tol(g)), atol=1e-12 * np.abs(F).max())
     cond = max(np.linalg.cond(L) ** 2 for L in g["L"])
     if cond < 1e9 or kind == "identity":
         prior = np.exp(g["theta"][:, 0]) + np.exp(g["theta"][:, -1])
@@ -355,3 +365,43 @@ def test_variance_closer_to_truth_than_reference(name):
         err_gpu, err_ref = np.abs(var_gpu - truth), np.abs(var_ref - truth)
         assert err_gpu.max() <= 1e-11 * prior[o], (o, err_gpu.max(), prior[o])
         assert err_gpu.max() <= max(err_ref.max(), 1e-13 * prior[o]), (o, err_gpu.max(), err_ref.max())
+
+
+@pytest.mark.parametrize("nu", [1, 3, 5, -1])
+@pytest.mark.parametrize("N,d,rows", [(40, 6, 1), (120, 6, 1000), (129, 20, 37), (256, 32, 530), (7, 3, 4096)])
+def test_small_batch_kernel_equals_chunked_path(nu, N, d, rows, monkeypatch):
+    """Value-only calls with n_train <= 256 and <= 4096 rows run in one fused kernel (csrc/small_eval.cuh);
+    AOED_SMALL_EVAL=0 sends the same call down the chunked xcov / triangular-product / epilogue path.  Same model, same
+    candidates: the two agree to rounding (different summation orders), for the surrogate outputs and every acquisition."""
+    import autooed_b200 as ab
+    from autooed_b200.problem import SimpleProblem
+    rng = np.random.default_rng(N + rows)
+    m = 2
+    X, Y = rng.random((N, d)), rng.standard_normal((N, m))
+    gp = ab.GaussianProcess(SimpleProblem(d, m), nu=nu)
+    theta = np.tile(np.concatenate([[0.3], np.log(rng.uniform(0.5, 2.0, d)), [-3.0]]), (m, 1))
+    gp.fit_fixed(X, Y, theta)
+    Xs = rng.random((rows, d))
+    Xs[0] = X[0]  # zero distance / near-zero variance
+    prior = np.exp(theta[0, 0]) + np.exp(theta[0, -1])
+    acqs = [ab.Identity(gp), ab.UpperConfidenceBound(gp), ab.ExpectedImprovement(gp), ab.ProbabilityOfImprovement(gp)]
+    for a in acqs:
+        a.fit(X, Y)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("AOED_SMALL_EVAL", mode)
+        out = gp.evaluate(Xs, std=True)
+        res[mode] = [out["F"], out["S"], gp.evaluate(Xs)["F"]] + [a.evaluate(Xs)[0] for a in acqs]
+    y_scale = Y.std(axis=0)
+    scale = np.abs(res["0"][0]).max()
+    # mean = sum_j k_j alpha_j: the two paths add the N terms in different orders, each term is up to prior * |alpha|
+    amax = max(np.abs(v.alpha_).max() for v in gp.gps)
+    mean_tol = max(1e-12 * scale, 4 * N * np.finfo(float).eps * amax * prior * y_scale.max())
+    assert np.abs(res["1"][0] - res["0"][0]).max() <= mean_tol
+    assert np.array_equal(res["1"][2], res["1"][0])                  # std=False call gives the same mean
+    # sigma = sqrt(prior - |w|^2): compare variances, the quantity the two paths sum differently
+    v1, v0 = (res["1"][1] / y_scale) ** 2, (res["0"][1] / y_scale) ** 2
+    assert np.abs(v1 - v0).max() <= 1e-12 * prior
+    ok = v0.min(axis=1) > 1e-6 * prior  # acquisitions divide by sigma: compare where sigma is not cancellation noise
+    for k in range(3, 7):
+        assert np.allclose(res["1"][k][ok], res["0"][k][ok], rtol=1e-8, atol=1e-10 * scale + 10 * mean_tol)
