@@ -32,7 +32,8 @@ def theta_bounds(n_var):
 
 
 class _LockstepLML:
-    """Runs one scipy L-BFGS-B per problem in its own thread; objective calls from all live threads are
+    """Fallback driver (used when scipy's private reverse-communication routine is not usable, see lbfgsb_lockstep.py):
+    runs one scipy L-BFGS-B per problem in its own thread; objective calls from all live threads are
     gathered and served by ONE batched device evaluation (`aoed_gp_lml_batch`)."""
 
     def __init__(self, evaluate_batch, n_prob):
@@ -221,6 +222,21 @@ class GaussianProcess(SurrogateModel):
         def evaluate_batch(ids, thetas):
             return self.log_marginal_likelihood_batch([obj_of[b] for b in ids], thetas, True)
 
+        import os
+        from autooed_b200.surrogate_model import lbfgsb_lockstep
+        if os.environ.get('AOED_FIT_DRIVER', 'lockstep') != 'threads' and lbfgsb_lockstep.available():
+            # scipy's own routine driven by reverse communication: same iterates, no thread hand-off per evaluation
+
+            def neg_batch(ids, thetas):
+                lml, grad = evaluate_batch(ids, thetas)
+                return -lml, -grad  # obj_func of _gpr.py:302-311
+
+            with single_threaded_blas():
+                results, n_batches, n_evals = lbfgsb_lockstep.minimize_lockstep(neg_batch, [p[1] for p in problems], bounds)
+            self.fit_info = {'n_problems': len(problems), 'n_batches': n_batches, 'n_lml_evals': n_evals,
+                             'nfev': [r[2] for r in results], 'driver': 'lockstep'}
+            return results
+
         pool = _LockstepLML(evaluate_batch, len(problems))
         results = [None] * len(problems)
 
@@ -245,7 +261,7 @@ class GaussianProcess(SurrogateModel):
             if isinstance(r, BaseException):
                 raise r
         self.fit_info = {'n_problems': len(problems), 'n_batches': pool.n_batches, 'n_lml_evals': pool.n_evals,
-                         'nfev': [r[2] for r in results]}
+                         'nfev': [r[2] for r in results], 'driver': 'threads'}
         return results
 
     @staticmethod

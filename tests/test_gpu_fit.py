@@ -165,3 +165,24 @@ def test_restarts_keep_best_and_batch_together():
         assert multi.gps[o].log_marginal_likelihood_value_ >= base.gps[o].log_marginal_likelihood_value_ - 1e-9
     # sklearn attribute surface after fit
     assert multi.gps[0].L_.shape == (40, 40) and multi.gps[0].alpha_.shape == (40,)
+
+
+@pytest.mark.parametrize("n_restarts", [0, 3])
+def test_lockstep_driver_equals_threaded_driver(n_restarts, monkeypatch):
+    """The fit drives scipy's L-BFGS-B routine by reverse communication in one thread (lbfgsb_lockstep.py);
+    AOED_FIT_DRIVER=threads runs `scipy.optimize.minimize` in one thread per problem instead.  Same routine, same
+    arguments, same device evaluations => identical hyper-parameters and evaluation counts."""
+    from autooed_b200 import GaussianProcess
+    from autooed_b200.problem import SimpleProblem
+    rng = np.random.default_rng(4)
+    X = rng.random((70, 5))
+    Y = np.stack([np.sin(3 * X[:, 0]) + X[:, 1] ** 2, np.cos(2 * X[:, 2]) * X[:, 3], X.sum(1)], 1)
+    out = {}
+    for driver in ("lockstep", "threads"):
+        monkeypatch.setenv("AOED_FIT_DRIVER", driver)
+        gp = GaussianProcess(SimpleProblem(5, 3), nu=5, n_restarts=n_restarts, seed=1)
+        gp.fit(X, Y)
+        assert gp.fit_info["driver"] == driver
+        out[driver] = (np.stack([g.kernel_.theta for g in gp.gps]), gp.fit_info["nfev"], gp.fit_info["n_lml_evals"])
+    assert np.array_equal(out["lockstep"][0], out["threads"][0])
+    assert out["lockstep"][1] == out["threads"][1] and out["lockstep"][2] == out["threads"][2]
