@@ -1171,7 +1171,13 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
     CU(cudaMemcpyAsync(gp->dObjB, h_obj, size_t(n_prob) * sizeof(int), cudaMemcpyHostToDevice, s0));
     const bool want_grad = h_grad != nullptr;
     const char* force = getenv("AOED_FIT_PATH");  // "blocked" forces the large-N path (tests)
-    const bool small = N <= FS_MAX_N && !(force && strcmp(force, "blocked") == 0);
+    static const bool force_v1 = getenv("AOED_FIT_SMALL") && strcmp(getenv("AOED_FIT_SMALL"), "v1") == 0;
+    const bool blk_fits = !force_v1 && lml_blk_smem(N, DP) <= 227 * 1024;
+    // One CTA per problem while the problem fits in shared memory.  Just above the blocked kernel's limit (N ~ 216) only
+    // the rank-1 kernel fits (~1 ms per launch): worth it for many problems at once, but a handful of problems is served
+    // faster by the multi-stream path (0.8 ms per round at N = 300).
+    const bool few = n_prob <= 6 && !force_v1 && !(force && strcmp(force, "small") == 0);
+    const bool small = N <= FS_MAX_N && !(force && strcmp(force, "blocked") == 0) && (blk_fits || !few);
     if (small) {
         // one CTA per problem, everything in shared memory
         LmlSmallArgs a;
@@ -1185,8 +1191,7 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
             a.clk = dclk;
         }
         // blocked DMMA kernel when its panel buffer fits beside the packed triangle (N <= ~208), else the rank-1 kernel
-        static const bool force_v1 = getenv("AOED_FIT_SMALL") && strcmp(getenv("AOED_FIT_SMALL"), "v1") == 0;
-        const bool blocked = !force_v1 && lml_blk_smem(N, DP) <= 227 * 1024;
+        const bool blocked = blk_fits;
         if (blocked) CHK(launch_lml_blk(gp->nu, DP, a, n_prob, s0));
         else CHK(launch_lml_small(gp->nu, DP, a, n_prob, s0));
         if (stamp) {
