@@ -104,3 +104,23 @@ def test_lockstep_driver_batches_all_problems():
     for b in range(n):
         assert np.allclose(res[b], [b, -b], atol=1e-5)
     assert sizes[0] == n and max(sizes) == n
+
+
+def test_argument_checks_need_no_device(lib):
+    """Invalid arguments are rejected before any CUDA call (the same codes on a box without a GPU)."""
+    import ctypes
+    cdll = lib.load()
+    F = np.zeros((4, 2))
+    rank, crowd, sel = np.zeros(4, np.int32), np.zeros(4), np.zeros(2, np.int32)
+    args = (lib.ptr(F), 2, lib.ptr(rank), lib.ptr(crowd), lib.ptr(sel))
+    assert cdll.aoed_nsga2_survival(0, 0, 2, *args) == lib.ERR_INVALID                       # no individuals
+    assert cdll.aoed_nsga2_survival(0, 4, 2, lib.ptr(F), 5, *args[2:]) == lib.ERR_INVALID    # keep > n
+    assert cdll.aoed_nsga2_survival(0, 4, 2, None, 2, *args[2:]) == lib.ERR_INVALID          # null objectives
+    assert cdll.aoed_nsga2_survival(0, 5000, 2, *args) == lib.ERR_UNSUPPORTED                # above the 4096-row limit
+    assert cdll.aoed_nsga2_survival(0, 4, 9, *args) == lib.ERR_UNSUPPORTED                   # more than 8 objectives
+    assert b"4096" in cdll.aoed_last_error()
+    n_out, n_eval = ctypes.c_int64(), ctypes.c_int64()
+    x = np.zeros((4, 3))
+    rc = cdll.aoed_nsga2_run(None, 0, 3, 2, 1, None, 4, lib.ptr(x), lib.ptr(x), lib.ptr(x), 8, 5, 1, lib.ptr(x), lib.ptr(F),
+                             ctypes.byref(n_out), ctypes.byref(n_eval))
+    assert rc == lib.ERR_INVALID  # null model handle
