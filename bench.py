@@ -558,6 +558,75 @@ def run_mobo_mode(args):
                   flush=True)
 
 
+def run_discovery_mode(args):
+    """BASELINE config c3 shape: the ParetoDiscovery inner loop on 100 samples — local optimisation,
+    KKT directions from the Hessians, first-order expansion — batched B200 path vs the per-sample CPU port
+    (oracle/discovery_oracle.py on the GP oracle), same model, same seed."""
+    from autooed_b200 import GaussianProcess, Identity
+    from autooed_b200.problem import SimpleProblem
+    from autooed_b200.solver.pareto_discovery import pareto_discover
+    from autooed_b200.surrogate_problem import SurrogateProblem
+    from oracle import discovery_oracle as do
+    from oracle import gp_oracle as go
+    ctx, threads = blas_threads()
+    d, m, N, pop, n_grid = 10, 2, 100, 100, 10
+    rng = np.random.default_rng(0)
+    X = rng.random((N, d))
+    f1 = X[:, 0]
+    gz = 1 + 9.0 / (d - 1) * X[:, 1:].sum(1)
+    Y = np.stack([f1, gz * (1 - np.sqrt(f1 / gz) - f1 / gz * np.sin(10 * np.pi * f1))], 1)  # ZDT3
+    prob = SimpleProblem(d, m)
+    gp = GaussianProcess(prob, nu=5)
+    gp.fit(X, Y)
+    acq = Identity(gp)
+    acq.fit(X, Y)
+    sp = SurrogateProblem(prob, acq)
+    calls = {"n": 0, "rows": 0}
+
+    def eval_func(x, return_values_of):
+        calls["n"] += 1
+        calls["rows"] += len(np.atleast_2d(x))
+        return sp.evaluate(x, return_values_of=return_values_of)
+
+    xs = rng.random((pop, d))
+    bounds = np.stack([np.zeros(d), np.ones(d)])
+    origin = Y.min(axis=0)
+    times = []
+    for rep in range(4):
+        np.random.seed(5)
+        calls["n"] = calls["rows"] = 0
+        t0 = time.perf_counter()
+        out = pareto_discover(xs, eval_func, bounds, None, 0.3, origin, 1e-2, n_grid)
+        times.append(time.perf_counter() - t0)
+    line = {"mode": "discovery", "arm": "b200", "what": "ParetoDiscovery inner loop, one generation", "samples": pop, "N": N,
+            "d": d, "m": m, "n_grid_sample": n_grid, "s_per_generation": min(times[1:]), "s_first": times[0],
+            "device_calls": calls["n"], "rows_per_call": calls["rows"] / max(calls["n"], 1), "patch_rows": int(len(out[0]))}
+    print(json.dumps(line), flush=True)
+    thetas = np.stack([g.kernel_.theta for g in gp.gps])
+    orc = go.GPOracle(d, m, nu=5).fit(X, Y, thetas=thetas)
+    n_cpu = 20
+    with ctx:
+        np.random.seed(5)
+        t0 = time.perf_counter()
+        ref = do.pareto_discover(xs[:n_cpu], do.oracle_eval_func(orc), bounds, 0.3, origin, 1e-2, n_grid)
+        dt = time.perf_counter() - t0
+    line = {"mode": "discovery", "arm": "cpu_port", "what": "the reference's per-sample loop on the GP oracle", "samples": n_cpu,
+            "s_measured": dt, "s_per_generation_extrapolated": dt * pop / n_cpu, "cpu_threads": threads}
+    # d > m: the minimiser of |F(x) - z| is a (d - m)-dimensional set, so the two arms' stopping POINTS may differ while
+    # the distance they reach agrees; compare that (each patch starts with its locally optimised sample)
+    from autooed_b200.solver.pareto_discovery import reference_point
+    np.random.seed(5)
+    small = pareto_discover(xs[:n_cpu], eval_func, bounds, None, 0.3, origin, 1e-2, n_grid)  # the same 20 samples on the GPU
+    x_gpu = small[0][np.r_[0, np.flatnonzero(np.diff(small[1])) + 1]]
+    ys = sp.evaluate(xs[:n_cpu], return_values_of=['F'])
+    zs = np.array([reference_point(y, y - small[3], 0.3) for y in ys])
+    reach = lambda xo: np.linalg.norm(sp.evaluate(xo, return_values_of=['F']) - zs, axis=1)
+    r_gpu, r_cpu = reach(x_gpu), reach(ref["x_opt"])
+    line["max_diff_of_reached_distance"] = float(np.abs(r_gpu - r_cpu).max())
+    line["mean_reached_distance"] = {"b200": float(r_gpu.mean()), "cpu_port": float(r_cpu.mean())}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -566,7 +635,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU per step (default 2^20)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sample budget per step")
-    ap.add_argument("--mode", default="evals", choices=["evals", "fit", "mobo"],
+    ap.add_argument("--mode", default="evals", choices=["evals", "fit", "mobo", "discovery"],
                     help="evals = the contract line (default); fit / mobo = secondary measurements, one JSON line each")
     ap.add_argument("--mobo-iters", type=int, default=20)
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS),
@@ -578,6 +647,8 @@ def main():
         return run_fit_mode(args)
     if args.mode == "mobo":
         return run_mobo_mode(args)
+    if args.mode == "discovery":
+        return run_discovery_mode(args)
     if args.impl == "reference":
         run_reference(args)
     else:
