@@ -35,7 +35,7 @@ struct SmallEvalArgs {
 };
 
 inline size_t small_eval_smem(int Npad, int DP) {
-    return (size_t(Npad) * SE_TC + size_t(Npad) * DP + size_t(Npad) + size_t(SE_TC) * DP + 16 * SE_TC) * sizeof(double);
+    return (size_t(Npad) * (SE_TC + 1) + size_t(Npad) * DP + size_t(Npad) + size_t(SE_TC) * (DP + 1) + 16 * SE_TC) * sizeof(double);
 }
 constexpr int SE_PF = 16;  // rows of L^-T in flight per thread: an L2 round trip is ~700 cycles, 16 rows of FMAs cover it
 
@@ -55,11 +55,13 @@ __device__ __forceinline__ double se_reduce(double v, double* red, int tid) {
 template <int NU, int DP>
 __global__ void __launch_bounds__(SE_THREADS) small_eval_kernel(SmallEvalArgs p) {
     extern __shared__ double se_smem[];
-    double* ks = se_smem;                          // [Npad][SE_TC]
-    double* ts = ks + size_t(p.Npad) * SE_TC;      // [Npad][DP] scaled training points of this objective
+    constexpr int XS = DP + 1;                     // odd row stride: the 16 candidates of a warp hit 16 different banks
+    constexpr int WS = SE_TC + 1;                  // row stride of the w buffer (same memory as ks, see step 2)
+    double* ks = se_smem;                          // [Npad][SE_TC] k*, later [Npad][WS] w
+    double* ts = ks + size_t(p.Npad) * WS;         // [Npad][DP] scaled training points of this objective
     double* al = ts + size_t(p.Npad) * DP;         // [Npad]
-    double* xs = al + p.Npad;                      // [SE_TC][DP]
-    double* red = xs + SE_TC * DP;                 // [8][SE_TC] (+ spare)
+    double* xs = al + p.Npad;                      // [SE_TC][XS]
+    double* red = xs + SE_TC * XS;                 // [8][SE_TC] (+ spare)
     const int tid = threadIdx.x, o = blockIdx.y;
     const int64_t c0 = int64_t(blockIdx.x) * SE_TC;
     const ModelDev md = p.model[o];
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(SE_THREADS) small_eval_kernel(SmallEvalArgs p)
     for (int t = tid; t < SE_TC * DP; t += SE_THREADS) {
         const int c = t / DP, k = t - c * DP;
         const int64_t row = min(c0 + c, p.rows - 1);  // dead candidates of the last tile repeat a valid row
-        xs[t] = k < p.d ? p.X[row * p.d + k] / p.ell[o * DP + k] : 0.0;
+        xs[c * XS + k] = k < p.d ? p.X[row * p.d + k] / p.ell[o * DP + k] : 0.0;
     }
     __syncthreads();
     // ---- 1. cross covariances and the mean --------------------------------------------------------------
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(SE_THREADS) small_eval_kernel(SmallEvalArgs p)
 #pragma unroll
         for (int k = 0; k < DP; k += 2) {
             const double2 t = *reinterpret_cast<const double2*>(ts + j * DP + k);
-            const double d0 = xs[c * DP + k] - t.x, d1 = xs[c * DP + k + 1] - t.y;
+            const double d0 = xs[c * XS + k] - t.x, d1 = xs[c * XS + k + 1] - t.y;
             r2 = fma(d0, d0, r2);
             r2b = fma(d1, d1, r2b);
         }
@@ -131,13 +133,13 @@ __global__ void __launch_bounds__(SE_THREADS) small_eval_kernel(SmallEvalArgs p)
             }
         }
         __syncthreads();  // everyone is done reading ks
-        if (i < p.N) {
+        if (i < p.N) {  // odd row stride: a warp's 32 rows spread over the banks instead of all landing on one
 #pragma unroll
-            for (int q = 0; q < SE_TC; ++q) ks[i * SE_TC + q] = acc[q];
+            for (int q = 0; q < SE_TC; ++q) ks[i * WS + q] = acc[q];
         }
         __syncthreads();
         for (int r = tid / SE_TC; r < p.N; r += SE_THREADS / SE_TC) {
-            const double w = ks[r * SE_TC + c];
+            const double w = ks[r * WS + c];
             ss = fma(w, w, ss);
         }
         ss = se_reduce(ss, red, tid);

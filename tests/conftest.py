@@ -16,8 +16,9 @@ def pytest_configure(config):
 
 def golden_files():
     """GP / acquisition fixtures (one per problem shape x nu); pareto_cases.npz is the multi-objective fixture, ts_*.npz
-    the Thompson-sampling ones, async_*.npz the penalised-acquisition ones."""
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("ts_", "pareto_", "async_")))
+    the Thompson-sampling ones, async_*.npz the penalised-acquisition ones, discovery_*.npz the ParetoDiscovery ones."""
+    other = ("ts_", "pareto_", "async_", "discovery_")
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(other))
 
 
 @pytest.fixture(scope="session")
