@@ -52,6 +52,8 @@ int pick_dp(int d) {
     if (d <= 16) return 16;
     if (d <= 24) return 24;
     if (d <= 32) return 32;
+    if (d <= 48) return 48;
+    if (d <= 64) return 64;
     return -1;
 }
 
@@ -274,7 +276,9 @@ void launch_xcov_any(int nu, int DP, const XcovArgs& a, dim3 grid, bool grad, cu
         case 8: launch_xcov_nu<8>(nu, a, grid, grad, s); break;
         case 16: launch_xcov_nu<16>(nu, a, grid, grad, s); break;
         case 24: launch_xcov_nu<24>(nu, a, grid, grad, s); break;
-        default: launch_xcov_nu<32>(nu, a, grid, grad, s); break;
+        case 32: launch_xcov_nu<32>(nu, a, grid, grad, s); break;
+        case 48: launch_xcov_nu<48>(nu, a, grid, grad, s); break;
+        default: launch_xcov_nu<64>(nu, a, grid, grad, s); break;
     }
 }
 
@@ -300,7 +304,9 @@ void query_occupancy(int nu, int DP, int& occ_xcov, int& occ_gradsum) {
         case 8: occ_xcov = occ_xcov_nu<8>(nu); occ_gradsum = occ_of(gradsum_kernel<8>, XC_THREADS); break;
         case 16: occ_xcov = occ_xcov_nu<16>(nu); occ_gradsum = occ_of(gradsum_kernel<16>, XC_THREADS); break;
         case 24: occ_xcov = occ_xcov_nu<24>(nu); occ_gradsum = occ_of(gradsum_kernel<24>, XC_THREADS); break;
-        default: occ_xcov = occ_xcov_nu<32>(nu); occ_gradsum = occ_of(gradsum_kernel<32>, XC_THREADS); break;
+        case 32: occ_xcov = occ_xcov_nu<32>(nu); occ_gradsum = occ_of(gradsum_kernel<32>, XC_THREADS); break;
+        case 48: occ_xcov = occ_xcov_nu<48>(nu); occ_gradsum = occ_of(gradsum_kernel<48>, XC_THREADS); break;
+        default: occ_xcov = occ_xcov_nu<64>(nu); occ_gradsum = occ_of(gradsum_kernel<64>, XC_THREADS); break;
     }
 }
 
@@ -309,7 +315,9 @@ void launch_gradsum(int DP, const GradsumArgs& a, dim3 grid, cudaStream_t s) {
         case 8: gradsum_kernel<8><<<grid, XC_THREADS, 0, s>>>(a); break;
         case 16: gradsum_kernel<16><<<grid, XC_THREADS, 0, s>>>(a); break;
         case 24: gradsum_kernel<24><<<grid, XC_THREADS, 0, s>>>(a); break;
-        default: gradsum_kernel<32><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 32: gradsum_kernel<32><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 48: gradsum_kernel<48><<<grid, XC_THREADS, 0, s>>>(a); break;
+        default: gradsum_kernel<64><<<grid, XC_THREADS, 0, s>>>(a); break;
     }
 }
 
@@ -319,7 +327,9 @@ void launch_kmat_dp(int DP, const KmatArgs& a, dim3 grid, cudaStream_t s) {
         case 8: kmat_kernel<NU, 8><<<grid, 256, 0, s>>>(a); break;
         case 16: kmat_kernel<NU, 16><<<grid, 256, 0, s>>>(a); break;
         case 24: kmat_kernel<NU, 24><<<grid, 256, 0, s>>>(a); break;
-        default: kmat_kernel<NU, 32><<<grid, 256, 0, s>>>(a); break;
+        case 32: kmat_kernel<NU, 32><<<grid, 256, 0, s>>>(a); break;
+        case 48: kmat_kernel<NU, 48><<<grid, 256, 0, s>>>(a); break;
+        default: kmat_kernel<NU, 64><<<grid, 256, 0, s>>>(a); break;
     }
 }
 
@@ -338,7 +348,9 @@ void launch_lmlgrad_dp(int DP, const LmlGradArgs& a, dim3 grid, cudaStream_t s) 
         case 8: lml_grad_kernel<NU, 8><<<grid, 256, 0, s>>>(a); break;
         case 16: lml_grad_kernel<NU, 16><<<grid, 256, 0, s>>>(a); break;
         case 24: lml_grad_kernel<NU, 24><<<grid, 256, 0, s>>>(a); break;
-        default: lml_grad_kernel<NU, 32><<<grid, 256, 0, s>>>(a); break;
+        case 32: lml_grad_kernel<NU, 32><<<grid, 256, 0, s>>>(a); break;
+        case 48: lml_grad_kernel<NU, 48><<<grid, 256, 0, s>>>(a); break;
+        default: lml_grad_kernel<NU, 64><<<grid, 256, 0, s>>>(a); break;
     }
 }
 
@@ -512,7 +524,9 @@ void launch_small_eval_dp(int DP, const SmallEvalArgs& a, dim3 grid, size_t smem
         case 8: launch_small_eval<NU, 8>(a, grid, smem, s); break;
         case 16: launch_small_eval<NU, 16>(a, grid, smem, s); break;
         case 24: launch_small_eval<NU, 24>(a, grid, smem, s); break;
-        default: launch_small_eval<NU, 32>(a, grid, smem, s); break;
+        case 32: launch_small_eval<NU, 32>(a, grid, smem, s); break;
+        case 48: launch_small_eval<NU, 48>(a, grid, smem, s); break;
+        default: launch_small_eval<NU, 64>(a, grid, smem, s); break;
     }
 }
 
@@ -621,7 +635,9 @@ void launch_hess_dp(int DP, const HessArgs& a, dim3 grid, cudaStream_t s) {
         case 8: hess_kernel<NU, 8><<<grid, HS_THREADS, 0, s>>>(a); break;
         case 16: hess_kernel<NU, 16><<<grid, HS_THREADS, 0, s>>>(a); break;
         case 24: hess_kernel<NU, 24><<<grid, HS_THREADS, 0, s>>>(a); break;
-        default: hess_kernel<NU, 32><<<grid, HS_THREADS, 0, s>>>(a); break;
+        case 32: hess_kernel<NU, 32><<<grid, HS_THREADS, 0, s>>>(a); break;
+        case 48: hess_kernel<NU, 48><<<grid, HS_THREADS, 0, s>>>(a); break;
+        default: hess_kernel<NU, 64><<<grid, HS_THREADS, 0, s>>>(a); break;
     }
 }
 
@@ -761,7 +777,7 @@ int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu) {
     if (n_var < 1 || n_obj < 1) return fail(AOED_ERR_INVALID, "n_var and n_obj must be positive");
     if (!(nu == 1 || nu == 3 || nu == 5 || nu == -1)) return fail(AOED_ERR_INVALID, "nu must be 1, 3, 5 or -1");
     const int DP = pick_dp(n_var);
-    if (DP < 0) return fail(AOED_ERR_UNSUPPORTED, "n_var > 32 is not supported yet");
+    if (DP < 0) return fail(AOED_ERR_UNSUPPORTED, "n_var > 64 is not supported");
     DeviceGuard guard_(device);
     CU(guard_.err);
     aoed_gp* gp = new aoed_gp();
@@ -1022,9 +1038,11 @@ int launch_lml_small_dp(int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t 
         FS_CASE(8)
         FS_CASE(16)
         FS_CASE(24)
+        FS_CASE(32)
+        FS_CASE(48)
         default:
-            CU(cudaFuncSetAttribute(lml_small_kernel<NU, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
-            lml_small_kernel<NU, 32><<<n_prob, FS_THREADS, sm, s>>>(a);
+            CU(cudaFuncSetAttribute(lml_small_kernel<NU, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
+            lml_small_kernel<NU, 64><<<n_prob, FS_THREADS, sm, s>>>(a);
             break;
     }
 #undef FS_CASE
@@ -1044,9 +1062,11 @@ int launch_lml_blk_dp(int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t s)
         FBK_CASE(8)
         FBK_CASE(16)
         FBK_CASE(24)
+        FBK_CASE(32)
+        FBK_CASE(48)
         default:
-            CU(cudaFuncSetAttribute(lml_blk_kernel<NU, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
-            lml_blk_kernel<NU, 32><<<n_prob, FS_THREADS, sm, s>>>(a);
+            CU(cudaFuncSetAttribute(lml_blk_kernel<NU, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
+            lml_blk_kernel<NU, 64><<<n_prob, FS_THREADS, sm, s>>>(a);
             break;
     }
 #undef FBK_CASE

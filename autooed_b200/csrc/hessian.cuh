@@ -59,11 +59,15 @@ struct GramArgs {
 };
 
 // one CTA per (candidate, objective); thread per (i, j) pair
+constexpr int GR_MAX_D = 64;
+constexpr int GR_PPT = GR_MAX_D * GR_MAX_D / HS_THREADS;  // (i, j) pairs per thread at the largest d
 __global__ void __launch_bounds__(HS_THREADS) gram_kernel(GramArgs p) {
-    __shared__ double w[64][33];
+    __shared__ double w[64][GR_MAX_D + 1];
     const int c = blockIdx.x, o = blockIdx.y, d = p.d;
     const double* __restrict__ W = p.W + o * p.strideSlab + int64_t(c) * d;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[GR_PPT];
+#pragma unroll
+    for (int u = 0; u < GR_PPT; ++u) acc[u] = 0.0;
     for (int t0 = 0; t0 < p.N; t0 += 64) {
         const int nt = min(64, p.N - t0);
         __syncthreads();
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(HS_THREADS) gram_kernel(GramArgs p) {
         }
         __syncthreads();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < GR_PPT; ++u) {
             const int pr = threadIdx.x + u * HS_THREADS;
             if (pr < d * d) {
                 const int i = pr / d, j = pr % d;
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(HS_THREADS) gram_kernel(GramArgs p) {
         }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < GR_PPT; ++u) {
         const int pr = threadIdx.x + u * HS_THREADS;
         if (pr < d * d) p.G[(int64_t(o) * p.rows + c) * d * d + pr] = acc[u];
     }
@@ -182,8 +186,9 @@ __device__ __forceinline__ void acq_second_order(const AcqDev& acq, int o, doubl
 template <int NU, int DP>
 __global__ void __launch_bounds__(HS_THREADS) hess_kernel(HessArgs p) {
     constexpr int PPT = (DP * DP + HS_THREADS - 1) / HS_THREADS;  // (i, j) pairs per thread
-    __shared__ double sS[HS_TT][DP + 1];   // s_t[i] = (x_i - t_i) / l_i^2
-    __shared__ double wB[2][HS_TT], wC[2][HS_TT];
+    constexpr int TT = DP > 32 ? HS_TT / 2 : HS_TT;  // the tile of s vectors has to stay inside 48 KB of static memory
+    __shared__ double sS[TT][DP + 1];   // s_t[i] = (x_i - t_i) / l_i^2
+    __shared__ double wB[2][TT], wC[2][TT];
     __shared__ double xs[DP], il[DP];
     __shared__ double redA[2][HS_THREADS / 32];
     const int tid = threadIdx.x;
@@ -204,9 +209,9 @@ __global__ void __launch_bounds__(HS_THREADS) hess_kernel(HessArgs p) {
     double sumA[2] = {0.0, 0.0};
     __syncthreads();
 
-    for (int t0 = 0; t0 < p.N; t0 += HS_TT) {
-        const int nt = min(HS_TT, p.N - t0);
-        if (tid < HS_TT) {
+    for (int t0 = 0; t0 < p.N; t0 += TT) {
+        const int nt = min(TT, p.N - t0);
+        if (tid < TT) {
             double cA = 0.0, cB = 0.0, cC = 0.0, al = 0.0, vv = 0.0;
             if (tid < nt) {
                 const double* tr = Ts + int64_t(t0 + tid) * DP;
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(HS_THREADS) hess_kernel(HessArgs p) {
             if (pr < d * d) {
                 const int i = pr / d, j = pr % d;
                 double b0 = accB[0][u], b1 = accB[1][u], c0 = accC[0][u], c1 = accC[1][u];
-                for (int t = 0; t < HS_TT; ++t) {
+                for (int t = 0; t < TT; ++t) {
                     const double sj = sS[t][j];
                     const double sij = sS[t][i] * sj, sjj = sj * sj;
                     b0 = fma(wB[0][t], sij, b0);

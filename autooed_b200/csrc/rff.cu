@@ -53,8 +53,8 @@ extern "C" int aoed_rff_eval(int device, int64_t n_rows, int n_var, int n_obj, i
         return rfail(AOED_ERR_INVALID, "bad argument");
     if (n_rows == 0) return AOED_OK;
     if (!h_Xn) return rfail(AOED_ERR_INVALID, "null input");
-    if (n_var > 32) return rfail(AOED_ERR_UNSUPPORTED, "n_var > 32 is not supported yet");
-    const int DP = n_var <= 8 ? 8 : n_var <= 16 ? 16 : n_var <= 24 ? 24 : 32;
+    if (n_var > 64) return rfail(AOED_ERR_UNSUPPORTED, "n_var > 64 is not supported");
+    const int DP = aoed::rff_dp(n_var);
     const size_t sm = (size_t(n_feat) * DP + 2 * size_t(n_feat)) * sizeof(double);
     if (sm > 200 * 1024) return rfail(AOED_ERR_UNSUPPORTED, "too many spectral points for shared memory");
     int ndev = 0;
@@ -106,12 +106,14 @@ extern "C" int aoed_rff_eval(int device, int64_t n_rows, int n_var, int n_obj, i
             RFF_CASE(8)
             RFF_CASE(16)
             RFF_CASE(24)
+            RFF_CASE(32)
+            RFF_CASE(48)
             default:
                 if (sm > 48 * 1024) {
-                    RCU(cudaFuncSetAttribute(rff_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
-                    RCU(cudaFuncSetAttribute(rff_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
+                    RCU(cudaFuncSetAttribute(rff_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
+                    RCU(cudaFuncSetAttribute(rff_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
                 }
-                launch_rff<32>(a, grad, grid, sm, nullptr);
+                launch_rff<64>(a, grad, grid, sm, nullptr);
                 break;
         }
 #undef RFF_CASE

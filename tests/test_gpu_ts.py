@@ -75,6 +75,33 @@ def test_large_population_vs_oracle_and_full_fit():
     assert np.isfinite(F).all() and np.isfinite(dF).all()
 
 
+@pytest.mark.parametrize("d", [40, 64])
+def test_more_than_32_variables(d):
+    """33 .. 64 design variables: the wider template instances of the fit, posterior and sample kernels, end to end
+    (fit on the device, Thompson sample value / gradient / Hessian against the oracle, host NSGA-II on top of it)."""
+    from autooed_b200 import GaussianProcess, NSGA2, ThompsonSampling
+    from autooed_b200.problem import SimpleProblem
+    rng = np.random.default_rng(d)
+    N, m = 60, 2
+    X = rng.random((N, d))
+    Y = np.sin(X @ rng.standard_normal((d, m)) / np.sqrt(d)) + 0.05 * rng.standard_normal((N, m))
+    prob = SimpleProblem(d, m)
+    gp = GaussianProcess(prob, nu=5)
+    gp.fit(X, Y)
+    acq = ThompsonSampling(gp)
+    np.random.seed(1)
+    acq.fit(X, Y)
+    Xs = rng.random((300, d))
+    F, dF, hF = acq.evaluate(Xs[:20], gradient=True, hessian=True)
+    ys = gp.normalization.y_scaler
+    oF, odF, ohF = to.ts_evaluate(Xs[:20], acq.thetas, acq.Ws, acq.bs, acq.sf2s, ys.mean_, ys.scale_, True, True)
+    assert np.allclose(F, oF, rtol=1e-10, atol=1e-10) and np.allclose(dF, odF, rtol=1e-9, atol=1e-9)
+    assert np.allclose(hF, ohF, rtol=1e-9, atol=1e-9)
+    np.random.seed(2)
+    Xc, Fc = NSGA2(prob, n_gen=5, pop_size=30).solve(X, Y, 4, acq)  # host loop: the device loop takes n_var <= 32
+    assert Xc.shape == (30, d) and np.allclose(Fc, acq.evaluate(Xc)[0], rtol=1e-10, atol=1e-10)
+
+
 def test_uncertainty_and_direct_selection():
     from autooed_b200 import Direct, GaussianProcess, Uncertainty
     from autooed_b200.problem import SimpleProblem
