@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) lml_grad_kernel(LmlGradArgs p) {
 
 // res[1 + k] = 0.5 * sum_blocks partial (k in the theta order [c1, l_1..l_d, c2]); zeros when the factorisation failed.
 // One CTA per component k (deterministic tree reduction).
-__global__ void __launch_bounds__(256) lml_grad_reduce_kernel(const double* __restrict__ partial, int nBlocks, int DP, int d,
+static __global__ void __launch_bounds__(256) lml_grad_reduce_kernel(const double* __restrict__ partial, int nBlocks, int DP, int d,
                                                               const int* info, double* res) {
     __shared__ double red[8];
     const int k = blockIdx.x;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) tri_matvec_kernel(const double* __restric
 }
 
 // Ts = X / l (padded to DP), c1c2 = exp(theta[0]), exp(theta[d+1]) for one hyper-parameter vector (device-side, no host sync)
-__global__ void theta_prep_kernel(const double* __restrict__ X, const double* __restrict__ theta, int N, int Npad, int d,
+static __global__ void theta_prep_kernel(const double* __restrict__ X, const double* __restrict__ theta, int N, int Npad, int d,
                                   int DP, double* __restrict__ Ts, double* __restrict__ c1c2) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx == 0) {
@@ -180,7 +180,7 @@ __global__ void theta_prep_kernel(const double* __restrict__ X, const double* __
 
 // res[0] = -1/2 y.alpha - sum log L_ii - N/2 log 2 pi   (_gpr.py:601-616); -inf when potrf reported a non-PD matrix
 // quad_a . quad_b is y . alpha (sklearn's form) or z . z with z = L^-1 y (same number, better conditioned)
-__global__ void __launch_bounds__(256) lml_value_kernel(const double* __restrict__ y, const double* __restrict__ alpha,
+static __global__ void __launch_bounds__(256) lml_value_kernel(const double* __restrict__ y, const double* __restrict__ alpha,
                                                         const double* __restrict__ Lfac, int N, int Npad, const int* info,
                                                         double* res) {
     __shared__ double red[2][8];
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) lml_value_kernel(const double* __restrict
 }
 
 // out[j][i] = in[i][j] for a square Npad matrix (batched via blockIdx.z)
-__global__ void transpose_square_kernel(const double* in, double* out, int n) {
+static __global__ void transpose_square_kernel(const double* in, double* out, int n) {
     __shared__ double tile[32][33];
     const double* src = in + int64_t(blockIdx.z) * n * n;
     double* dst = out + int64_t(blockIdx.z) * n * n;
@@ -225,14 +225,14 @@ __global__ void transpose_square_kernel(const double* in, double* out, int n) {
 }
 
 // keeps the lower triangle (row-major, rows/cols < N) and zeroes everything else
-__global__ void keep_lower_kernel(double* A, int N, int Npad) {
+static __global__ void keep_lower_kernel(double* A, int N, int Npad) {
     double* M = A + int64_t(blockIdx.z) * Npad * Npad;
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (j >= Npad) return;
     if (i >= N || j >= N || j > i) M[int64_t(i) * Npad + j] = 0.0;
 }
 
-__global__ void set_identity_kernel(double* A, int N, int Npad) {
+static __global__ void set_identity_kernel(double* A, int N, int Npad) {
     double* M = A + int64_t(blockIdx.z) * Npad * Npad;
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (j >= Npad) return;

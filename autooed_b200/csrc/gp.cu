@@ -16,6 +16,7 @@
 #include "fit.cuh"
 #include "fit_small.cuh"
 #include "fit_small2.cuh"
+#include "fit_launch.h"
 #include "hessian.cuh"
 #include "posterior.cuh"
 #include "small_eval.cuh"
@@ -1026,72 +1027,6 @@ int ensure_fit_ctx(aoed_gp* gp) {
     return AOED_OK;
 }
 
-template <int NU>
-int launch_lml_small_dp(int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t s) {
-    const size_t sm = lml_small_smem(a.N, DP);
-#define FS_CASE(D)                                                                                              \
-    case D:                                                                                                     \
-        CU(cudaFuncSetAttribute(lml_small_kernel<NU, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm))); \
-        lml_small_kernel<NU, D><<<n_prob, FS_THREADS, sm, s>>>(a);                                              \
-        break;
-    switch (DP) {
-        FS_CASE(8)
-        FS_CASE(16)
-        FS_CASE(24)
-        FS_CASE(32)
-        FS_CASE(48)
-        default:
-            CU(cudaFuncSetAttribute(lml_small_kernel<NU, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
-            lml_small_kernel<NU, 64><<<n_prob, FS_THREADS, sm, s>>>(a);
-            break;
-    }
-#undef FS_CASE
-    CU(cudaGetLastError());
-    return AOED_OK;
-}
-
-template <int NU>
-int launch_lml_blk_dp(int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t s) {
-    const size_t sm = lml_blk_smem(a.N, DP);
-#define FBK_CASE(D)                                                                                            \
-    case D:                                                                                                    \
-        CU(cudaFuncSetAttribute(lml_blk_kernel<NU, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm))); \
-        lml_blk_kernel<NU, D><<<n_prob, FS_THREADS, sm, s>>>(a);                                               \
-        break;
-    switch (DP) {
-        FBK_CASE(8)
-        FBK_CASE(16)
-        FBK_CASE(24)
-        FBK_CASE(32)
-        FBK_CASE(48)
-        default:
-            CU(cudaFuncSetAttribute(lml_blk_kernel<NU, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
-            lml_blk_kernel<NU, 64><<<n_prob, FS_THREADS, sm, s>>>(a);
-            break;
-    }
-#undef FBK_CASE
-    CU(cudaGetLastError());
-    return AOED_OK;
-}
-
-int launch_lml_blk(int nu, int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t s) {
-    switch (nu) {
-        case 1: return launch_lml_blk_dp<1>(DP, a, n_prob, s);
-        case 3: return launch_lml_blk_dp<3>(DP, a, n_prob, s);
-        case 5: return launch_lml_blk_dp<5>(DP, a, n_prob, s);
-        default: return launch_lml_blk_dp<-1>(DP, a, n_prob, s);
-    }
-}
-
-int launch_lml_small(int nu, int DP, const LmlSmallArgs& a, int n_prob, cudaStream_t s) {
-    switch (nu) {
-        case 1: return launch_lml_small_dp<1>(DP, a, n_prob, s);
-        case 3: return launch_lml_small_dp<3>(DP, a, n_prob, s);
-        case 5: return launch_lml_small_dp<5>(DP, a, n_prob, s);
-        default: return launch_lml_small_dp<-1>(DP, a, n_prob, s);
-    }
-}
-
 }  // namespace
 
 extern "C" {
@@ -1212,8 +1147,8 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
         }
         // blocked DMMA kernel when its panel buffer fits beside the packed triangle (N <= ~208), else the rank-1 kernel
         const bool blocked = blk_fits;
-        if (blocked) CHK(launch_lml_blk(gp->nu, DP, a, n_prob, s0));
-        else CHK(launch_lml_small(gp->nu, DP, a, n_prob, s0));
+        if (blocked) CU(aoed::launch_lml_blk(gp->nu, DP, a, n_prob, s0));
+        else CU(aoed::launch_lml_small(gp->nu, DP, a, n_prob, s0));
         if (stamp) {
             long long h[8];
             CU(cudaMemcpyAsync(h, dclk, sizeof(h), cudaMemcpyDeviceToHost, s0));
