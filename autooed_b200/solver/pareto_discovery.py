@@ -49,8 +49,9 @@ def local_optimization_batched(xs, zs, eval_func, bounds):
 
     def evaluate_batch(ids, X):
         F, dF = eval_func(X, return_values_of=['F', 'dF'])  # one device call for all live runs
-        out = [_distance_and_gradient(F[k], dF[k], zs[i]) for k, i in enumerate(ids)]
-        return np.array([o[0] for o in out]), np.stack([o[1] for o in out])
+        diff = F - zs[ids]
+        dist = np.sqrt(np.einsum('km,km->k', diff, diff))
+        return dist, np.einsum('km,kmd->kd', diff / dist[:, None], dF)
 
     results, _, _ = lbfgsb_lockstep.minimize_lockstep(evaluate_batch, list(xs), box)
     return np.array([r[0] for r in results])

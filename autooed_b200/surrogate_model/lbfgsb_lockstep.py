@@ -19,7 +19,17 @@ _GTOL = 1e-5
 _MAXCOR, _MAXLS, _MAXFUN, _MAXITER = 10, 20, 15000, 15000
 _TASK_FG, _TASK_NEW_X = 3, 1
 
+_FACTR = _FTOL / np.finfo(float).eps
 _checked = None
+_setulb_fn = None
+
+
+def _setulb():
+    global _setulb_fn
+    if _setulb_fn is None:
+        from scipy.optimize import _lbfgsb
+        _setulb_fn = _lbfgsb.setulb
+    return _setulb_fn
 
 
 class _Run:
@@ -54,12 +64,10 @@ class _Run:
 
     def advance(self):
         """Runs the optimiser until it asks for f, g at `self.x` (returns True) or stops (returns False)."""
-        from scipy.optimize import _lbfgsb
-        factr = _FTOL / np.finfo(float).eps
-        while True:
-            self.g = self.g.astype(np.float64)
-            _lbfgsb.setulb(_MAXCOR, self.x, self.low, self.up, self.nbd, self.f, self.g, factr, _GTOL, self.wa, self.iwa,
-                           self.task, self.lsave, self.isave, self.dsave, _MAXLS, self.ln_task)
+        setulb = _setulb()
+        while True:  # (scipy re-casts g to float64 on every pass; `feed` already guarantees that type)
+            setulb(_MAXCOR, self.x, self.low, self.up, self.nbd, self.f, self.g, _FACTR, _GTOL, self.wa, self.iwa,
+                   self.task, self.lsave, self.isave, self.dsave, _MAXLS, self.ln_task)
             if self.task[0] == _TASK_FG:
                 return True
             if self.task[0] == _TASK_NEW_X:
@@ -73,7 +81,7 @@ class _Run:
             return False
 
     def feed(self, f, g):
-        self.f, self.g = float(f), np.array(g, dtype=np.float64)
+        self.f, self.g = float(f), np.array(g, dtype=np.float64)  # own contiguous float64 copy
         self.nfev += 1
 
 
