@@ -123,50 +123,43 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_blk_kernel(LmlSmallArgs p) 
         const int k0 = kb * FB;
         if (warp == 0) {
             const long long tdiag0 = (p.clk != nullptr) ? clock64() : 0;
-            // diagonal block -> Dsm (lower; identity padding beyond N), unblocked Cholesky, then its inverse -> Dinv
-            for (int e = lane; e < FB * FB; e += 32) {
-                const int r = e / FB, c = e % FB;
+            // diagonal block (lower; identity padding beyond N): unblocked Cholesky with row r of the block in the
+            // registers of lane r (lanes 16..31 mirror 0..15) and the pivot column passed around by shuffles — the chain
+            // per pivot is one shuffle, one rsqrt, one multiply, one shuffle, one FMA instead of three shared-memory
+            // round trips.  Same operations in the same order as the shared-memory version it replaces.  Then -> Dsm for
+            // the inverse below.
+            const int r = lane & 15;
+            double a[FB];
+#pragma unroll
+            for (int c = 0; c < FB; ++c) {
                 double v = 0.0;
                 if (c <= r) v = (k0 + r < N) ? Lp[tri(k0 + r) + k0 + c] : (r == c ? 1.0 : 0.0);
-                Dsm[r * (FB + 1) + c] = v;
+                a[c] = v;
+            }
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < FB; ++c) {
+                if (!bad) {
+                    const double dcc = __shfl_sync(0xffffffffu, a[c], c);
+                    if (!(dcc > 0.0)) {
+                        bad = true;  // the same value in every lane: uniform
+                    } else {
+                        const double ip = rsqrt(dcc);
+                        a[c] = (r == c) ? dcc * ip : a[c] * ip;  // L_rc (rows above the pivot hold 0)
+                        if (lane == c) Dinv[c * (FB + 1) + c] = ip;  // 1 / L_cc
+#pragma unroll
+                        for (int cc = c + 1; cc < FB; ++cc) {
+                            const double lcc = __shfl_sync(0xffffffffu, a[c], cc);  // L_{cc,c}
+                            if (cc <= r) a[cc] = fma(-a[c], lcc, a[cc]);
+                        }
+                    }
+                }
+            }
+            if (lane < FB) {
+#pragma unroll
+                for (int c = 0; c < FB; ++c) Dsm[lane * (FB + 1) + c] = a[c];
             }
             __syncwarp();
-            bool bad = false;
-            for (int c = 0; c < FB; ++c) {
-                const double dcc = Dsm[c * (FB + 1) + c];
-                if (!(dcc > 0.0)) {
-                    bad = true;
-                    break;
-                }
-                const double ip = rsqrt(dcc);
-                __syncwarp();
-                const int r = lane & 15, h = lane >> 4;
-                if (h == 0 && r > c) Dsm[r * (FB + 1) + c] *= ip;
-                if (lane == 0) {
-                    Dsm[c * (FB + 1) + c] = dcc * ip;
-                    Dinv[c * (FB + 1) + c] = ip;  // 1 / L_cc
-                }
-                __syncwarp();
-                if (r > c) {
-                    // all loads first (independent), then the multiply-adds and stores: the chain per pivot is what bounds
-                    // this warp, and the compiler cannot reorder shared-memory reads across the writes by itself
-                    const double lrc = Dsm[r * (FB + 1) + c];
-                    double lc[FB / 2], av[FB / 2];
-#pragma unroll
-                    for (int t = 0; t < FB / 2; ++t) {
-                        const int cc = c + 1 + h + 2 * t;
-                        const bool on = cc <= r;
-                        lc[t] = on ? Dsm[cc * (FB + 1) + c] : 0.0;
-                        av[t] = on ? Dsm[r * (FB + 1) + cc] : 0.0;
-                    }
-#pragma unroll
-                    for (int t = 0; t < FB / 2; ++t) {
-                        const int cc = c + 1 + h + 2 * t;
-                        if (cc <= r) Dsm[r * (FB + 1) + cc] = fma(-lrc, lc[t], av[t]);
-                    }
-                }
-                __syncwarp();
-            }
             const long long tdiag1 = (p.clk != nullptr) ? clock64() : 0;
             if (p.clk != nullptr && lane == 0) p.clk[int64_t(b) * 8 + 6] = (kb == 0 ? 0 : p.clk[int64_t(b) * 8 + 6]) + (tdiag1 - tdiag0);
             if (bad) {
