@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libaoed_b200.so")
-SOURCES = ["gp.cu", "fit_launch.cu", "moo.cu", "rff.cu", "nsga2.cu"]
+SOURCES = ["gp.cu", "blocked.cu", "fit_launch.cu", "moo.cu", "rff.cu", "nsga2.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "aoed_b200.h")]
 
 
@@ -37,14 +37,14 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "5"]  # the sources compile concurrently
+           "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "6"]  # the sources compile concurrently
     for macro in ("AOED_XCOV_UNROLL", "AOED_XCOV_MINBLOCKS", "AOED_XCOV_XS_SMEM"):  # tuning experiments; defaults live in posterior.cuh
         if os.environ.get(macro):
             cmd += [f"-D{macro}={os.environ[macro]}"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ["-lcusolver", "-lcublas", "-o", LIB]
+    cmd += ["-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -1,8 +1,6 @@
 // Host side of the C ABI for the GP surrogate: handle, device residency, launch orchestration.
 // See include/aoed_b200.h for the contract of every exported function.
-#include <cublas_v2.h>
 #include <cuda_runtime.h>
-#include <cusolverDn.h>
 
 #include <cmath>
 #include <cstdio>
@@ -13,6 +11,7 @@
 #include <vector>
 
 #include "../../include/aoed_b200.h"
+#include "blocked.h"
 #include "fit.cuh"
 #include "fit_small.cuh"
 #include "fit_small2.cuh"
@@ -74,19 +73,6 @@ struct Workspace {
 
 }  // namespace
 
-// per-stream scratch of the blocked (large-N) log-marginal-likelihood path
-struct FitCtx {
-    cudaStream_t stream = nullptr;
-    cusolverDnHandle_t solver = nullptr;
-    double *K = nullptr, *Ts = nullptr, *c1c2 = nullptr, *alpha = nullptr, *partial = nullptr, *work = nullptr;
-    double *Linv = nullptr, *LinvT = nullptr, *Kinv = nullptr, *z = nullptr;  // own K^-1 = L^-T L^-1 (persistent TRMM)
-    cublasHandle_t blas = nullptr;
-    CUtensorMap mapLinvT, mapLinv;
-    int* info = nullptr;
-    int lwork = 0;
-};
-constexpr int kMaxFitCtx = 6;
-
 struct aoed_gp {
     int device = 0, d = 0, m = 0, nu = 1, DP = 8;
     int N = 0, Npad = 0, Kpad = 0, mTiles = 0, JS = 1, jchunk = 0;  // JS: CAPACITY of the training-index split (partials)
@@ -98,22 +84,18 @@ struct aoed_gp {
     double *dX = nullptr, *dY = nullptr;  // [N][d], [m][Npad]
     double *dTs = nullptr, *dAlpha = nullptr, *dEll = nullptr, *dLinv = nullptr, *dLinvT = nullptr, *dL = nullptr;
     ModelDev* dModel = nullptr;
-    // fit scratch
-    double *dK = nullptr, *dC1C2 = nullptr, *dGradPartial = nullptr, *dGrad = nullptr;
-    int* dInfo = nullptr;
-    double* dSolverWork = nullptr;
-    int solverLwork = 0;
-    cusolverDnHandle_t solver = nullptr;
-    cublasHandle_t blas = nullptr;
+    double* dC1C2 = nullptr;        // [m][2]
     CUtensorMap mapLinv, mapLinvT;  // TMA views of the cached factors (A operands)
     int* dTickets = nullptr;        // tile ticket counters of the persistent triangular products
     int* hDbg = nullptr;            // host-mapped diagnostics of the persistent kernel (AOED_TRMM_DEBUG=1)
     int ticket_slot = 0;
     int trmm_variant = 0;           // 0: persistent TMA kernel, 64 / 128: cp.async tiled kernel with that column tile
     int ssf = PT_SS_PER_TILE;       // sum-of-squares partials per 128-row tile (4 for the TMA kernel, 1 otherwise)
-    FitCtx fit[kMaxFitCtx];
-    int nfit = 0;        // contexts with a stream + handle
-    int nfit_sized = 0;  // ... of which have buffers for the current capacity
+    // blocked factorisation (blocked.cu): tile plan of the current matrix size, one batch of matrices, per-problem vectors
+    BlockedPlan plan;
+    BlockedMats mats;
+    double *bTs = nullptr, *bC1C2 = nullptr, *bZ = nullptr, *bAlpha = nullptr, *bPartial = nullptr;
+    int *bInfo = nullptr, *bCounters = nullptr;
     double *dThetaB = nullptr, *dResB = nullptr;  // batched LML inputs / results
     int* dObjB = nullptr;
     int batchCap = 0;
@@ -145,29 +127,28 @@ void free_ws(Workspace& w) {
     w.hrows = 0;
 }
 
+void free_blocked(aoed_gp* gp) {
+    blocked_mats_free(gp->mats);
+    blocked_plan_free(gp->plan);
+    double** ptrs[] = {&gp->bTs, &gp->bC1C2, &gp->bZ, &gp->bAlpha, &gp->bPartial};
+    for (auto pp : ptrs) {
+        if (*pp) cudaFree(*pp);
+        *pp = nullptr;
+    }
+    if (gp->bInfo) cudaFree(gp->bInfo);
+    if (gp->bCounters) cudaFree(gp->bCounters);
+    gp->bInfo = gp->bCounters = nullptr;
+}
+
 void free_model(aoed_gp* gp) {
-    double** ptrs[] = {&gp->dX, &gp->dY, &gp->dTs, &gp->dAlpha, &gp->dEll, &gp->dLinv, &gp->dLinvT, &gp->dL,
-                       &gp->dK, &gp->dC1C2, &gp->dGradPartial, &gp->dGrad, &gp->dSolverWork};
+    double** ptrs[] = {&gp->dX, &gp->dY, &gp->dTs, &gp->dAlpha, &gp->dEll, &gp->dLinv, &gp->dLinvT, &gp->dL, &gp->dC1C2};
     for (auto pp : ptrs) {
         if (*pp) cudaFree(*pp);
         *pp = nullptr;
     }
     if (gp->dModel) cudaFree(gp->dModel);
     gp->dModel = nullptr;
-    if (gp->dInfo) cudaFree(gp->dInfo);
-    gp->dInfo = nullptr;
-    for (int i = 0; i < gp->nfit; ++i) {
-        FitCtx& c = gp->fit[i];
-        double** fp[] = {&c.K, &c.Ts, &c.c1c2, &c.alpha, &c.partial, &c.work, &c.Linv, &c.LinvT, &c.Kinv, &c.z};
-        for (auto pp : fp) {
-            if (*pp) cudaFree(*pp);
-            *pp = nullptr;
-        }
-        if (c.info) cudaFree(c.info);
-        c.info = nullptr;
-        c.lwork = 0;
-    }
-    gp->nfit_sized = 0;  // streams and cuSOLVER handles survive (creating a handle costs tens of milliseconds)
+    free_blocked(gp);
     gp->cap_Npad = 0;
     if (gp->dThetaB) cudaFree(gp->dThetaB);
     if (gp->dResB) cudaFree(gp->dResB);
@@ -192,7 +173,6 @@ int64_t chunk_cap(bool device_resident = false) {
 }
 
 int make_map_2d(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
-int size_fit_ctx_work(aoed_gp* gp, FitCtx& c);
 
 int ensure_ws(aoed_gp* gp, Workspace& w, int64_t cols, bool staging) {
     cols = round_up64(cols, 128);
@@ -412,6 +392,14 @@ int make_map_2d(CUtensorMap* map, const double* base, int64_t rows, int64_t cols
     if (r != CUDA_SUCCESS) return fail(AOED_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
     return AOED_OK;
 }
+
+}  // namespace
+namespace aoed {
+int make_tensor_map_2d(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    return make_map_2d(map, base, rows, cols, ld, box_rows);
+}
+}  // namespace aoed
+namespace {
 
 int trmm_variant_from_env() {
     const char* e = getenv("AOED_TRMM");
@@ -796,8 +784,6 @@ int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu) {
     }
     CU(cudaEventCreate(&gp->ev0));
     CU(cudaEventCreate(&gp->ev1));
-    if (cusolverDnCreate(&gp->solver) != CUSOLVER_STATUS_SUCCESS) return fail(AOED_ERR_CUDA, "cusolverDnCreate failed");
-    if (cublasCreate(&gp->blas) != CUBLAS_STATUS_SUCCESS) return fail(AOED_ERR_CUDA, "cublasCreate failed");
     *out = gp;
     return AOED_OK;
 }
@@ -807,14 +793,6 @@ int aoed_gp_destroy(aoed_gp_t* gp) {
     DeviceGuard guard_(gp->device);
     cudaDeviceSynchronize();
     free_model(gp);
-    for (int i = 0; i < gp->nfit; ++i) {
-        if (gp->fit[i].solver) cusolverDnDestroy(gp->fit[i].solver);
-        if (gp->fit[i].blas) cublasDestroy(gp->fit[i].blas);
-        if (gp->fit[i].stream) cudaStreamDestroy(gp->fit[i].stream);
-    }
-    gp->nfit = 0;
-    if (gp->solver) cusolverDnDestroy(gp->solver);
-    if (gp->blas) cublasDestroy(gp->blas);
     if (gp->ev0) cudaEventDestroy(gp->ev0);
     if (gp->ev1) cudaEventDestroy(gp->ev1);
     for (auto& s : gp->streams)
@@ -868,18 +846,12 @@ int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const doub
         CU(cudaMalloc(&gp->dLinv, size_t(m) * Np * Np * sizeof(double)));
         CU(cudaMalloc(&gp->dLinvT, size_t(m) * Np * Np * sizeof(double)));
         CU(cudaMalloc(&gp->dL, size_t(m) * Np * Np * sizeof(double)));
-        CU(cudaMalloc(&gp->dTickets, (64 + kMaxFitCtx) * sizeof(int)));  // ring for the compute stream + one per fit context
+        CU(cudaMalloc(&gp->dTickets, 64 * sizeof(int)));  // ring for the compute stream
         if (gp->trmm_variant == 0) {
             CHK(make_map_2d(&gp->mapLinv, gp->dLinv, int64_t(m) * Np, Np, Np, TM));
             CHK(make_map_2d(&gp->mapLinvT, gp->dLinvT, int64_t(m) * Np, Np, Np, TM));
         }
-        CU(cudaMalloc(&gp->dK, Np * Np * sizeof(double)));
         CU(cudaMalloc(&gp->dC1C2, size_t(m) * 2 * sizeof(double)));
-        CU(cudaMalloc(&gp->dInfo, sizeof(int)));
-        const size_t nbp = (Np + 15) / 16;
-        CU(cudaMalloc(&gp->dGradPartial, nbp * nbp * (gp->DP + 2) * sizeof(double)));
-        CU(cudaMalloc(&gp->dGrad, size_t(gp->DP + 2) * sizeof(double)));
-        gp->solverLwork = 0;
         gp->cap_Npad = gp->Npad;
     } else if (prevN != N) {
         // slab rows in [N, Kpad) feed the triangular products as k-rows against zero columns of the factor: keep them
@@ -899,18 +871,6 @@ int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const doub
     for (int o = 0; o < m; ++o)
         for (int i = 0; i < N; ++i) yt[size_t(o) * Np + i] = h_Yn[size_t(i) * m + o];
     CU(cudaMemcpy(gp->dY, yt.data(), yt.size() * sizeof(double), cudaMemcpyHostToDevice));
-    int lwork = 0;
-    if (cusolverDnDpotrf_bufferSize(gp->solver, CUBLAS_FILL_MODE_UPPER, N, gp->dK, gp->Npad, &lwork) !=
-        CUSOLVER_STATUS_SUCCESS)
-        return fail(AOED_ERR_CUDA, "potrf_bufferSize failed");
-    if (lwork > gp->solverLwork || gp->dSolverWork == nullptr) {
-        if (gp->dSolverWork) cudaFree(gp->dSolverWork);
-        gp->dSolverWork = nullptr;
-        CU(cudaMalloc(&gp->dSolverWork, size_t(std::max(lwork, 1)) * sizeof(double)));
-        gp->solverLwork = std::max(lwork, 1);
-    }
-    // per-stream cuSOLVER scratch of the blocked LML path follows N as well
-    for (int i = 0; i < gp->nfit_sized; ++i) CHK(size_fit_ctx_work(gp, gp->fit[i]));
     return AOED_OK;
 }
 
@@ -935,29 +895,6 @@ int upload_theta_slot(aoed_gp* gp, int slot, const double* theta, cudaStream_t s
     return AOED_OK;
 }
 
-// K(theta) of objective slot -> gp->dK, Cholesky in place (row-major lower).  info != 0 => not PD.
-int factor_slot(aoed_gp* gp, int slot, int* info, cudaStream_t s) {
-    const int N = gp->N, Npad = gp->Npad;
-    CU(cudaMemsetAsync(gp->dK, 0, size_t(Npad) * Npad * sizeof(double), s));
-    KmatArgs ka;
-    ka.Ts = gp->dTs + size_t(slot) * Npad * gp->DP;
-    ka.c1c2 = gp->dC1C2 + size_t(slot) * 2;
-    ka.K = gp->dK; ka.N = N; ka.Npad = Npad; ka.DP = gp->DP;
-    const int nb = (N + 15) / 16;
-    launch_kmat(gp->nu, gp->DP, ka, dim3(nb, nb, 1), s);
-    gp->n_launches++;
-    CU(cudaGetLastError());
-    cusolverDnSetStream(gp->solver, s);
-    // row-major lower L  <=>  column-major upper U = L^T with K = U^T U
-    if (cusolverDnDpotrf(gp->solver, CUBLAS_FILL_MODE_UPPER, N, gp->dK, Npad, gp->dSolverWork, gp->solverLwork,
-                         gp->dInfo) != CUSOLVER_STATUS_SUCCESS)
-        return fail(AOED_ERR_CUDA, "cusolverDnDpotrf failed");
-    CU(cudaMemcpyAsync(info, gp->dInfo, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    return AOED_OK;
-}
-
-
 int ensure_batch(aoed_gp* gp, int n_prob) {
     if (gp->batchCap >= n_prob) return AOED_OK;
     if (gp->dThetaB) cudaFree(gp->dThetaB);
@@ -972,58 +909,64 @@ int ensure_batch(aoed_gp* gp, int n_prob) {
     return AOED_OK;
 }
 
-// cuSOLVER's potrf is a long chain of small launches (latency bound even at N = 2000): run several problems side by side
-int fit_ctx_count(int N) { return N <= 4096 ? kMaxFitCtx : 2; }
-
-int size_fit_ctx_work(aoed_gp* gp, FitCtx& c) {
-    int l1 = 0, l2 = 0;
-    if (cusolverDnDpotrf_bufferSize(c.solver, CUBLAS_FILL_MODE_UPPER, gp->N, c.K, gp->Npad, &l1) != CUSOLVER_STATUS_SUCCESS ||
-        cusolverDnDpotri_bufferSize(c.solver, CUBLAS_FILL_MODE_UPPER, gp->N, c.K, gp->Npad, &l2) != CUSOLVER_STATUS_SUCCESS)
-        return fail(AOED_ERR_CUDA, "cusolver bufferSize failed");
-    const int need = std::max(std::max(l1, l2), 1);
-    if (need > c.lwork || c.work == nullptr) {
-        if (c.work) cudaFree(c.work);
-        c.work = nullptr;
-        CU(cudaMalloc(&c.work, size_t(need) * sizeof(double)));
-        c.lwork = need;
+// Scratch of the blocked factorisation for up to `want` problems side by side (fewer when the budget — AOED_FIT_SCRATCH_GB,
+// default 16 GB, and half of the free device memory — says so; the callers loop over groups of gp->mats.cap problems).
+int ensure_blocked(aoed_gp* gp, int want) {
+    const int Npad = gp->Npad, DP = gp->DP;
+    if (gp->plan.T * TM != Npad) CHK(blocked_plan_build(gp->plan, Npad / TM));
+    const size_t per = 4 * size_t(Npad) * Npad * sizeof(double);
+    const char* e = getenv("AOED_FIT_SCRATCH_GB");
+    double budget = (e ? atof(e) : 16.0) * double(1ull << 30);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const double held = double(gp->mats.cap) * double(per);  // what this handle already holds counts as available
+        budget = std::min(budget, 0.5 * (double(free_b) + held));
     }
+    const int cap_max = std::max(1, int(budget / double(per)));
+    const int cap = std::min(std::max(want, 1), cap_max);
+    if (gp->mats.Npad == Npad && gp->mats.cap >= cap) return AOED_OK;
+    blocked_mats_free(gp->mats);
+    double** ptrs[] = {&gp->bTs, &gp->bC1C2, &gp->bZ, &gp->bAlpha, &gp->bPartial};
+    for (auto pp : ptrs) {
+        if (*pp) cudaFree(*pp);
+        *pp = nullptr;
+    }
+    if (gp->bInfo) cudaFree(gp->bInfo);
+    if (gp->bCounters) cudaFree(gp->bCounters);
+    gp->bInfo = gp->bCounters = nullptr;
+    CHK(blocked_mats_alloc(gp->mats, Npad, cap));
+    const size_t nbp = size_t(Npad) / KM_T;
+    CU(cudaMalloc(&gp->bTs, size_t(cap) * Npad * DP * sizeof(double)));
+    CU(cudaMalloc(&gp->bC1C2, size_t(cap) * 2 * sizeof(double)));
+    CU(cudaMalloc(&gp->bZ, size_t(cap) * Npad * sizeof(double)));
+    CU(cudaMalloc(&gp->bAlpha, size_t(cap) * Npad * sizeof(double)));
+    CU(cudaMalloc(&gp->bPartial, size_t(cap) * nbp * nbp * (DP + 2) * sizeof(double)));
+    CU(cudaMalloc(&gp->bInfo, size_t(cap) * sizeof(int)));
+    CU(cudaMalloc(&gp->bCounters, size_t(gp->plan.n_counters) * sizeof(int)));
     return AOED_OK;
 }
 
-int ensure_fit_ctx(aoed_gp* gp) {
-    const int Npad = gp->Npad, DP = gp->DP;
-    const int n = fit_ctx_count(gp->N);
-    const size_t NN = size_t(Npad) * Npad;
-    const size_t nbp = (size_t(Npad) + 15) / 16;
-    for (int i = gp->nfit; i < n; ++i) {  // streams + handles: created once per model handle
-        FitCtx& c = gp->fit[i];
-        CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-        if (cusolverDnCreate(&c.solver) != CUSOLVER_STATUS_SUCCESS) return fail(AOED_ERR_CUDA, "cusolverDnCreate failed");
-        cusolverDnSetStream(c.solver, c.stream);
-        if (cublasCreate(&c.blas) != CUBLAS_STATUS_SUCCESS) return fail(AOED_ERR_CUDA, "cublasCreate failed");
-        cublasSetStream(c.blas, c.stream);
-        gp->nfit = i + 1;
-    }
-    for (int i = gp->nfit_sized; i < gp->nfit; ++i) {  // buffers: per row capacity
-        FitCtx& c = gp->fit[i];
-        CU(cudaMalloc(&c.K, NN * sizeof(double)));
-        CU(cudaMemsetAsync(c.K, 0, NN * sizeof(double), c.stream));
-        CU(cudaMalloc(&c.Ts, size_t(Npad) * DP * sizeof(double)));
-        CU(cudaMalloc(&c.c1c2, 2 * sizeof(double)));
-        CU(cudaMalloc(&c.alpha, size_t(Npad) * sizeof(double)));
-        CU(cudaMalloc(&c.partial, nbp * nbp * (DP + 2) * sizeof(double)));
-        CU(cudaMalloc(&c.info, 2 * sizeof(int)));
-        CU(cudaMalloc(&c.z, size_t(Npad) * sizeof(double)));
-        if (gp->trmm_variant == 0) {
-            CU(cudaMalloc(&c.Linv, NN * sizeof(double)));
-            CU(cudaMalloc(&c.LinvT, NN * sizeof(double)));
-            CU(cudaMalloc(&c.Kinv, NN * sizeof(double)));
-            CHK(make_map_2d(&c.mapLinvT, c.LinvT, Npad, Npad, Npad, TM));  // A operand of the UPPER product
-            CHK(make_map_2d(&c.mapLinv, c.Linv, Npad, Npad, Npad, TK));    // B operand: the N columns of L^-1
-        }
-        CHK(size_fit_ctx_work(gp, c));
-        gp->nfit_sized = i + 1;
-    }
+// One group of G <= gp->mats.cap problems on stream s:  K(theta) -> L (mats.K), L^-1 (mats.X), L^-T (mats.XT),
+// z = L^-1 y (bZ), alpha = L^-T z (`alpha_out`, stride Npad), bInfo[b] != 0 where K is not positive definite.
+//   d_Ts [G][Npad][DP], d_c1c2 [G][2]: scaled inputs / kernel constants of the G problems; d_obj [G]: which y each uses.
+int blocked_group(aoed_gp* gp, int G, const double* d_Ts, const double* d_c1c2, const int* d_obj, double* alpha_out,
+                  cudaStream_t s) {
+    const int N = gp->N, Npad = gp->Npad, DP = gp->DP;
+    const int64_t NN = int64_t(Npad) * Npad;
+    BlockedMats& mt = gp->mats;
+    KmatArgs ka;
+    ka.Ts = d_Ts; ka.c1c2 = d_c1c2; ka.K = mt.K; ka.N = N; ka.Npad = Npad; ka.DP = DP; ka.pad = 1;
+    const int nbk = Npad / KM_T;
+    launch_kmat(gp->nu, DP, ka, dim3(nbk, nbk, G), s);
+    gp->n_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(gp->bInfo, 0, size_t(G) * sizeof(int), s));
+    CHK(blocked_chol_inverse(gp->plan, mt, G, gp->bInfo, gp->bCounters, sm_count(gp->device), s, &gp->n_launches));
+    transpose_square_kernel<<<dim3(Npad / 32, Npad / 32, G), dim3(32, 8), 0, s>>>(mt.X, mt.XT, Npad);
+    tri_matvec_kernel<false><<<dim3((N + 7) / 8, G), 256, 0, s>>>(mt.X, NN, gp->dY, Npad, d_obj, N, Npad, gp->bZ, Npad);
+    tri_matvec_kernel<true><<<dim3((N + 7) / 8, G), 256, 0, s>>>(mt.XT, NN, gp->bZ, Npad, nullptr, N, Npad, alpha_out, Npad);
+    gp->n_launches += 3;
+    CU(cudaGetLastError());
     return AOED_OK;
 }
 
@@ -1037,60 +980,56 @@ int aoed_gp_set_theta(aoed_gp_t* gp, const double* h_theta) {
     DeviceGuard guard_(gp->device);
     CU(guard_.err);
     cudaStream_t s = gp->streams[0];
-    const int N = gp->N, Npad = gp->Npad, m = gp->m, d = gp->d, p = d + 2;
+    const int N = gp->N, Npad = gp->Npad, m = gp->m, d = gp->d, p = d + 2, DP = gp->DP;
     const size_t NN = size_t(Npad) * Npad;
     gp->theta.assign(h_theta, h_theta + size_t(m) * p);
     gp->has_theta = false;
-    cublasSetStream(gp->blas, s);
     std::vector<ModelDev> md(m);
     for (int o = 0; o < m; ++o) {
         const double* th = h_theta + size_t(o) * p;
         CHK(upload_theta_slot(gp, o, th, s));
-        int info = 0;
-        CHK(factor_slot(gp, o, &info, s));
-        if (info != 0)
-            return fail(AOED_ERR_NOT_PD, "kernel matrix of objective " + std::to_string(o) +
-                                             " is not positive definite at the given theta (leading minor " +
-                                             std::to_string(info) + ")");
-        double* L = gp->dL + o * NN;
-        CU(cudaMemcpyAsync(L, gp->dK, NN * sizeof(double), cudaMemcpyDeviceToDevice, s));
-        keep_lower_kernel<<<dim3((Npad + 127) / 128, Npad, 1), 128, 0, s>>>(L, N, Npad);
-        // alpha = K^-1 y
-        double* alpha = gp->dAlpha + size_t(o) * Npad;
-        CU(cudaMemcpyAsync(alpha, gp->dY + size_t(o) * Npad, size_t(Npad) * sizeof(double), cudaMemcpyDeviceToDevice, s));
-        if (cusolverDnDpotrs(gp->solver, CUBLAS_FILL_MODE_UPPER, N, 1, gp->dK, Npad, alpha, Npad, gp->dInfo) !=
-            CUSOLVER_STATUS_SUCCESS)
-            return fail(AOED_ERR_CUDA, "cusolverDnDpotrs failed");
-        // L^-1 (row-major) = column-major U^-1 :  solve U X = I
-        double* Linv = gp->dLinv + o * NN;
-        set_identity_kernel<<<dim3((Npad + 127) / 128, Npad, 1), 128, 0, s>>>(Linv, N, Npad);
-        const double one = 1.0;
-        if (cublasDtrsm(gp->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, N, N,
-                        &one, gp->dK, Npad, Linv, Npad) != CUBLAS_STATUS_SUCCESS)
-            return fail(AOED_ERR_CUDA, "cublasDtrsm failed");
-        keep_lower_kernel<<<dim3((Npad + 127) / 128, Npad, 1), 128, 0, s>>>(Linv, N, Npad);
-        transpose_square_kernel<<<dim3(Npad / 32, Npad / 32, 1), dim3(32, 8), 0, s>>>(Linv, gp->dLinvT + o * NN, Npad);
-        gp->n_launches += 4;
-        CU(cudaGetLastError());
-        // log marginal likelihood value at theta (_gpr.py:601-616)
-        std::vector<double> hal(N), hdiag(N);
-        CU(cudaMemcpyAsync(hal.data(), alpha, size_t(N) * sizeof(double), cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpy2DAsync(hdiag.data(), sizeof(double), L, (size_t(Npad) + 1) * sizeof(double), sizeof(double), N,
-                             cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        double quad = 0.0, logdet = 0.0;
-        for (int i = 0; i < N; ++i) {
-            quad += gp->Yn[size_t(i) * m + o] * hal[i];
-            logdet += log(hdiag[i]);
-        }
-        gp->lml[o] = -0.5 * quad - logdet - 0.5 * N * log(2.0 * M_PI);
         md[o].c1 = exp(th[0]);
         md[o].c2 = exp(th[d + 1]);
         md[o].y_mean = gp->y_mean[o];
         md[o].y_scale = gp->y_scale[o];
     }
+    // all objectives side by side through the blocked factorisation (groups when the scratch budget is smaller than m)
+    CHK(ensure_batch(gp, m));
+    CHK(ensure_blocked(gp, m));
+    std::vector<int> iota(m);
+    for (int o = 0; o < m; ++o) iota[o] = o;
+    CU(cudaMemcpyAsync(gp->dObjB, iota.data(), size_t(m) * sizeof(int), cudaMemcpyHostToDevice, s));
+    std::vector<double> res(size_t(m) * (p + 1));
+    std::vector<int> info(m, 0);
+    const int cap = gp->mats.cap;
+    for (int o0 = 0; o0 < m; o0 += cap) {
+        const int G = std::min(cap, m - o0);
+        double* alpha = gp->dAlpha + size_t(o0) * Npad;
+        CHK(blocked_group(gp, G, gp->dTs + size_t(o0) * Npad * DP, gp->dC1C2 + size_t(o0) * 2, gp->dObjB + o0, alpha, s));
+        // log marginal likelihood value at theta (_gpr.py:601-616)
+        lml_value_kernel<<<G, 256, 0, s>>>(gp->bZ, gp->bZ, gp->mats.K, N, Npad, gp->bInfo, gp->dResB + size_t(o0) * (p + 1), p + 1);
+        // cached state: L_ (lower), L^-1 and its transpose, zero outside the N x N lower triangle
+        double* L = gp->dL + o0 * NN;
+        double* Linv = gp->dLinv + o0 * NN;
+        CU(cudaMemcpyAsync(L, gp->mats.K, size_t(G) * NN * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CU(cudaMemcpyAsync(Linv, gp->mats.X, size_t(G) * NN * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        keep_lower_kernel<<<dim3((Npad + 127) / 128, Npad, G), 128, 0, s>>>(L, N, Npad);
+        keep_lower_kernel<<<dim3((Npad + 127) / 128, Npad, G), 128, 0, s>>>(Linv, N, Npad);
+        transpose_square_kernel<<<dim3(Npad / 32, Npad / 32, G), dim3(32, 8), 0, s>>>(Linv, gp->dLinvT + o0 * NN, Npad);
+        gp->n_launches += 4;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(info.data() + o0, gp->bInfo, size_t(G) * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    for (int o = 0; o < m; ++o)
+        if (info[o] != 0)
+            return fail(AOED_ERR_NOT_PD, "kernel matrix of objective " + std::to_string(o) +
+                                             " is not positive definite at the given theta (leading minor " +
+                                             std::to_string(info[o]) + ")");
+    CU(cudaMemcpyAsync(res.data(), gp->dResB, res.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(gp->dModel, md.data(), m * sizeof(ModelDev), cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));
+    for (int o = 0; o < m; ++o) gp->lml[o] = res[size_t(o) * (p + 1)];
     gp->has_theta = true;
     return AOED_OK;
 }
@@ -1162,80 +1101,31 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
         gp->n_launches++;
         gp->n_fit_small += n_prob;
     } else {
-        CHK(ensure_fit_ctx(gp));
-        const int nctx = std::min(gp->nfit_sized, fit_ctx_count(N));
-        CU(cudaStreamSynchronize(s0));  // thetas uploaded
-        const int nb = (N + 15) / 16;
-        for (int b = 0; b < n_prob; ++b) {
-            FitCtx& c = gp->fit[b % nctx];
-            cudaStream_t s = c.stream;
-            const int o = h_obj[b];
-            double* res = gp->dResB + size_t(b) * (p + 1);
-            theta_prep_kernel<<<(Npad * DP + 255) / 256, 256, 0, s>>>(gp->dX, gp->dThetaB + size_t(b) * p, N, Npad, d, DP,
-                                                                     c.Ts, c.c1c2);
-            KmatArgs ka;
-            ka.Ts = c.Ts; ka.c1c2 = c.c1c2; ka.K = c.K; ka.N = N; ka.Npad = Npad; ka.DP = DP;
-            launch_kmat(gp->nu, DP, ka, dim3(nb, nb, 1), s);
-            CU(cudaGetLastError());
-            // row-major lower L  <=>  column-major upper U = L^T with K = U^T U
-            if (cusolverDnDpotrf(c.solver, CUBLAS_FILL_MODE_UPPER, N, c.K, Npad, c.work, c.lwork, c.info) !=
-                CUSOLVER_STATUS_SUCCESS)
-                return fail(AOED_ERR_CUDA, "cusolverDnDpotrf failed");
-            const double* yo = gp->dY + size_t(o) * Npad;
-            if (gp->trmm_variant == 0) {
-                // L^-1 once (cuBLAS trsm against I), then everything else is products with it:
-                //   z = L^-1 y, alpha = L^-T z, lml from z.z;  K^-1 = L^-T L^-1 on the persistent DMMA kernel
-                // (N^3/3 + N^3 useful flops instead of potrs + potri's ~520 small launches per problem)
-                set_identity_kernel<<<dim3((Npad + 127) / 128, Npad, 1), 128, 0, s>>>(c.Linv, N, Npad);
-                const double one = 1.0;
-                if (cublasDtrsm(c.blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, N, N, &one,
-                                c.K, Npad, c.Linv, Npad) != CUBLAS_STATUS_SUCCESS)
-                    return fail(AOED_ERR_CUDA, "cublasDtrsm failed");
-                keep_lower_kernel<<<dim3((Npad + 127) / 128, Npad, 1), 128, 0, s>>>(c.Linv, N, Npad);
-                transpose_square_kernel<<<dim3(Npad / 32, Npad / 32, 1), dim3(32, 8), 0, s>>>(c.Linv, c.LinvT, Npad);
-                tri_matvec_kernel<false><<<(N + 7) / 8, 256, 0, s>>>(c.Linv, yo, N, Npad, c.z);
-                tri_matvec_kernel<true><<<(N + 7) / 8, 256, 0, s>>>(c.LinvT, c.z, N, Npad, c.alpha);
-                lml_value_kernel<<<1, 256, 0, s>>>(c.z, c.z, c.K, N, Npad, c.info, res);
-                gp->n_launches += 8;
-                if (want_grad) {
-                    TrmmArgs t;
-                    t.A = c.LinvT; t.strideA = 0; t.lda = Npad;
-                    t.B = c.Linv; t.strideB = 0; t.ldb = Npad;
-                    t.Out = c.Kinv; t.strideOut = 0; t.ldo = Npad;
-                    t.sumsq = nullptr; t.strideSS = 0;
-                    t.M = N; t.Kpad = gp->Kpad; t.mTiles = gp->mTiles;
-                    CHK(launch_trmm_tma<true>(gp, c.mapLinvT, c.mapLinv, t, Npad / TN, 1, s, gp->dTickets + 64 + (b % nctx)));
-                    LmlGradArgs ga;
-                    ga.Ts = c.Ts; ga.c1c2 = c.c1c2; ga.alpha = c.alpha; ga.Kinv = c.Kinv; ga.partial = c.partial;
-                    ga.N = N; ga.Npad = Npad; ga.DP = DP; ga.nBlocksX = nb; ga.nBlocksY = nb;
-                    launch_lmlgrad(gp->nu, DP, ga, dim3(nb, nb, 1), s);
-                    lml_grad_reduce_kernel<<<DP + 2, 256, 0, s>>>(c.partial, nb * nb, DP, d, c.info, res);
-                    gp->n_launches += 3;
-                }
-                CU(cudaGetLastError());
-                continue;
-            }
-            CU(cudaMemcpyAsync(c.alpha, yo, size_t(Npad) * sizeof(double), cudaMemcpyDeviceToDevice, s));
-            if (cusolverDnDpotrs(c.solver, CUBLAS_FILL_MODE_UPPER, N, 1, c.K, Npad, c.alpha, Npad, c.info + 1) !=
-                CUSOLVER_STATUS_SUCCESS)
-                return fail(AOED_ERR_CUDA, "cusolverDnDpotrs failed");
-            lml_value_kernel<<<1, 256, 0, s>>>(gp->dY + size_t(o) * Npad, c.alpha, c.K, N, Npad, c.info, res);
-            gp->n_launches += 3;
+        // blocked factorisation, all problems of a group side by side in every launch (blocked.cu)
+        CHK(ensure_blocked(gp, n_prob));
+        const int cap = gp->mats.cap;
+        for (int g0 = 0; g0 < n_prob; g0 += cap) {
+            const int G = std::min(cap, n_prob - g0);
+            double* res = gp->dResB + size_t(g0) * (p + 1);
+            theta_prep_kernel<<<dim3((Npad * DP + 255) / 256, G), 256, 0, s0>>>(gp->dX, gp->dThetaB + size_t(g0) * p, N, Npad, d,
+                                                                                DP, gp->bTs, gp->bC1C2);
+            gp->n_launches++;
+            CHK(blocked_group(gp, G, gp->bTs, gp->bC1C2, gp->dObjB + g0, gp->bAlpha, s0));
+            // lml = -1/2 z.z - sum log L_ii - N/2 log 2 pi with z = L^-1 y (the same number as y.alpha, better conditioned)
+            lml_value_kernel<<<G, 256, 0, s0>>>(gp->bZ, gp->bZ, gp->mats.K, N, Npad, gp->bInfo, res, p + 1);
+            gp->n_launches++;
             if (want_grad) {
-                // K^-1 from the factor in place (N^3 2/3 flops instead of sklearn's cho_solve against I, _gpr.py:631-633)
-                if (cusolverDnDpotri(c.solver, CUBLAS_FILL_MODE_UPPER, N, c.K, Npad, c.work, c.lwork, c.info + 1) !=
-                    CUSOLVER_STATUS_SUCCESS)
-                    return fail(AOED_ERR_CUDA, "cusolverDnDpotri failed");
+                CHK(blocked_kinv(gp->plan, gp->mats, G, gp->bCounters, sm_count(gp->device), s0, &gp->n_launches));
                 LmlGradArgs ga;
-                ga.Ts = c.Ts; ga.c1c2 = c.c1c2; ga.alpha = c.alpha; ga.Kinv = c.K; ga.partial = c.partial;
+                ga.Ts = gp->bTs; ga.c1c2 = gp->bC1C2; ga.alpha = gp->bAlpha; ga.Kinv = gp->mats.P; ga.partial = gp->bPartial;
+                const int nb = (N + KM_T - 1) / KM_T;  // blocks beyond nb x nb hold padding only
                 ga.N = N; ga.Npad = Npad; ga.DP = DP; ga.nBlocksX = nb; ga.nBlocksY = nb;
-                launch_lmlgrad(gp->nu, DP, ga, dim3(nb, nb, 1), s);
-                lml_grad_reduce_kernel<<<DP + 2, 256, 0, s>>>(c.partial, nb * nb, DP, d, c.info, res);
+                launch_lmlgrad(gp->nu, DP, ga, dim3(nb, nb, G), s0);
+                lml_grad_reduce_kernel<<<dim3(DP + 2, G), 256, 0, s0>>>(gp->bPartial, nb * nb, DP, d, gp->bInfo, res);
                 gp->n_launches += 2;
             }
             CU(cudaGetLastError());
         }
-        for (int i = 0; i < nctx; ++i) CU(cudaStreamSynchronize(gp->fit[i].stream));
         gp->n_fit_blocked += n_prob;
     }
     std::vector<double> res(size_t(n_prob) * (p + 1));
