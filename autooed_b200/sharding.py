@@ -76,6 +76,43 @@ def evaluate_sharded(fn, X, group=None, gather=True):
     return g(local)
 
 
+def evaluate_sharded_device(gp, d_X, n_rows, acq_kind, acq_param, gradient=True, group=None, out=None):
+    """Device-resident sharded acquisition evaluation with an NCCL all-gather of the results.
+
+    `d_X` is a float64 CUDA tensor (n_rows, n_var) of NORMALISED candidates replicated on every rank (the solver's
+    population); each rank evaluates the contiguous shard `shard_bounds(n_rows, world, rank)` through
+    `aoed_gp_eval_device` straight into its slice of the gathered output tensors, then ONE `all_gather_into_tensor`
+    per output (value: n_rows x m, gradient: n_rows x m x d) runs over NVLink.  No host staging anywhere.
+    Returns (A, dA, timings) with timings = {'compute_ms', 'gather_ms'} measured with CUDA events on the current stream.
+    `out` = (A, dA) re-uses gathered tensors of a previous call (their row count is world * ceil(n_rows / world))."""
+    ws, rank = world(group)
+    m, d = gp.n_obj, gp.n_var
+    per = -(-n_rows // ws)
+    dev = d_X.device
+    if out is None:
+        A = torch.empty((ws * per, m), dtype=torch.float64, device=dev)
+        dA = torch.empty((ws * per, m, d), dtype=torch.float64, device=dev) if gradient else None
+    else:
+        A, dA = out
+    lo, hi = shard_bounds(n_rows, ws, rank)
+    a_loc = A[rank * per:(rank + 1) * per]
+    da_loc = dA[rank * per:(rank + 1) * per] if gradient else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    if hi > lo:
+        gp.evaluate_device(d_X[lo:hi], hi - lo, std=True, gradient=gradient, acq_kind=acq_kind, acq_param=acq_param,
+                           d_A=a_loc, d_dA=da_loc, stream=stream)
+    e1.record()
+    if ws > 1:
+        dist.all_gather_into_tensor(A, a_loc, group=group)  # in place: every rank's slice lands at its offset
+        if gradient:
+            dist.all_gather_into_tensor(dA, da_loc, group=group)
+    e2.record()
+    e2.synchronize()
+    return A[:n_rows], (dA[:n_rows] if gradient else None), {'compute_ms': e0.elapsed_time(e1), 'gather_ms': e1.elapsed_time(e2)}
+
+
 def fit_sharded(gp, X, Y, dtype='raw', group=None):
     """`GaussianProcess.fit` with the (objective x restart) problems distributed over the ranks.  Every rank ends
     with the same fitted model (the winning thetas are gathered, each rank factorises locally)."""
@@ -148,8 +185,11 @@ def hvi_select_sharded(Y_candidate, Y, batch_size, contrib_fn=None, front_fn=Non
         for v, i in pairs:  # rank order = ascending index ranges, strict '>' keeps the lowest index
             if i >= 0 and v > best_v:
                 best_v, best_i = v, int(i)
-        if best_i < 0:  # no positive contribution anywhere: the reference's random pick (hvi.py:38-39), same on every
-            best_i = int(np.random.choice(np.flatnonzero(free)))  # rank because the global RNG state is replicated
+        if best_i < 0:  # no positive contribution anywhere: the reference's random pick (hvi.py:38-39), drawn on rank 0 and
+            pick = [int(np.random.choice(np.flatnonzero(free)))]  # broadcast — the ranks' numpy RNG states need not agree
+            if ws > 1:
+                dist.broadcast_object_list(pick, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            best_i = pick[0]
         free[best_i] = False
         front = np.vstack([front, Yc[best_i]])
         chosen.append(best_i)

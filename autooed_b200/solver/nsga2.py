@@ -47,10 +47,16 @@ class NSGA2Algorithm:
         self.n_eval = 0
 
     # -- variation -------------------------------------------------------------------------------------------------
-    def _tournament(self, rank, crowd, n):
+    def _tournament(self, rank, crowd, n, cv=None):
+        """Binary tournament (pymoo `binary_tournament`): if either contestant violates a constraint the smaller violation
+        wins (random on ties); between feasible ones rank, then crowding distance, random on ties."""
         a, b = np.random.randint(len(rank), size=n), np.random.randint(len(rank), size=n)
         better = (rank[a] < rank[b]) | ((rank[a] == rank[b]) & (crowd[a] > crowd[b]))
         tie = (rank[a] == rank[b]) & (crowd[a] == crowd[b])
+        if cv is not None:
+            infeas = (cv[a] > 0.0) | (cv[b] > 0.0)
+            better = np.where(infeas, cv[a] < cv[b], better)
+            tie = np.where(infeas, cv[a] == cv[b], tie)
         pick_a = np.where(tie, np.random.rand(n) < 0.5, better)
         return np.where(pick_a, a, b)
 
@@ -114,20 +120,46 @@ class NSGA2Algorithm:
             crowd[idx] = crowding_distance(F[idx])
         return rank, crowd
 
-    def _survive(self, X, F):
-        rank, crowd = self._rank_and_crowding(F)
-        if len(X) > self.pop_size:
-            order = np.lexsort((-crowd, rank))[:self.pop_size]  # fronts in order, last front by crowding descending
-            X, F, rank, crowd = X[order], F[order], rank[order], crowd[order]
-        return X, F, rank, crowd
+    def _survive(self, X, F, cv=None):
+        """Rank-and-crowding survival.  With constraints (pymoo `Survival.do`, filter_infeasible=True): the feasible
+        individuals compete by rank and crowding for the `pop_size` places; places left over go to the infeasible ones
+        in order of increasing violation (they carry the rank after the last feasible front and zero crowding)."""
+        if cv is None or not (cv > 0.0).any():
+            rank, crowd = self._rank_and_crowding(F)
+            if len(X) > self.pop_size:
+                order = np.lexsort((-crowd, rank))[:self.pop_size]  # fronts in order, last front by crowding descending
+                X, F, rank, crowd = X[order], F[order], rank[order], crowd[order]
+                cv = None if cv is None else cv[order]
+            return X, F, rank, crowd, cv
+        feas, infeas = np.flatnonzero(cv <= 0.0), np.flatnonzero(cv > 0.0)
+        keep, rank, crowd = np.empty(0, dtype=int), np.empty(0, dtype=int), np.empty(0)
+        if len(feas):
+            r, c = self._rank_and_crowding(F[feas])
+            order = np.lexsort((-c, r))[:self.pop_size]
+            keep, rank, crowd = feas[order], r[order], c[order]
+        room = min(self.pop_size, len(X)) - len(keep)
+        if room > 0:
+            worst = infeas[np.argsort(cv[infeas], kind='stable')[:room]]
+            base = (rank.max() + 1) if len(rank) else 0
+            keep = np.concatenate([keep, worst])
+            rank = np.concatenate([rank, np.full(len(worst), base, dtype=int)])
+            crowd = np.concatenate([crowd, np.zeros(len(worst))])
+        return X[keep], F[keep], rank, crowd, cv[keep]
+
+    def _evaluate(self, problem, X, constrained):
+        if not constrained:
+            return np.asarray(problem.evaluate(X, return_values_of=['F'])), None
+        F, CV = problem.evaluate(X, return_values_of=['F', 'CV'])
+        return np.asarray(F), np.asarray(CV, dtype=float).reshape(-1)
 
     # -- driver ----------------------------------------------------------------------------------------------------
     def minimize(self, problem, X0, n_gen):
         xl, xu = np.asarray(problem.xl, dtype=float), np.asarray(problem.xu, dtype=float)
+        constrained = getattr(problem, 'n_constr', 0) > 0
         X = np.array(X0, dtype=float)
-        F = np.asarray(problem.evaluate(X, return_values_of=['F']))
+        F, cv = self._evaluate(problem, X, constrained)
         self.n_eval = len(X)
-        X, F, rank, crowd = self._survive(X, F)
+        X, F, rank, crowd, cv = self._survive(X, F, cv)
         for _ in range(n_gen - 1):
             off = np.empty((0, X.shape[1]))
             for _attempt in range(10):  # refill after duplicate elimination, as pymoo's mating loop does
@@ -135,16 +167,17 @@ class NSGA2Algorithm:
                 if need <= 0:
                     break
                 n_pairs = (need + 1) // 2
-                pa = self._tournament(rank, crowd, n_pairs)
-                pb = self._tournament(rank, crowd, n_pairs)
+                pa = self._tournament(rank, crowd, n_pairs, cv)
+                pb = self._tournament(rank, crowd, n_pairs, cv)
                 c1, c2 = self._sbx(X[pa], X[pb], xl, xu)
                 cand = self._mutate(np.vstack([c1, c2])[:need], xl, xu)
                 off = np.vstack([off, self._drop_duplicates(cand, np.vstack([X, off]))])
             if len(off) == 0:
                 break
-            Foff = np.asarray(problem.evaluate(off, return_values_of=['F']))
+            Foff, cvoff = self._evaluate(problem, off, constrained)
             self.n_eval += len(off)
-            X, F, rank, crowd = self._survive(np.vstack([X, off]), np.vstack([F, Foff]))
+            X, F, rank, crowd, cv = self._survive(np.vstack([X, off]), np.vstack([F, Foff]),
+                                                  None if cv is None else np.concatenate([cv, cvoff]))
         return X, F
 
 

@@ -53,6 +53,44 @@ def test_nsga2_converges_and_keeps_invariants():
     assert mo.check_pareto(F).mean() > 0.9
 
 
+class ConstrainedZdt1(Zdt1):
+    """ZDT1 with the cheap constraint x0 + x1 >= 0.6 (G <= 0 is feasible), pymoo `Problem.evaluate` protocol."""
+    n_constr = 1
+
+    def evaluate(self, X, return_values_of=None):
+        F = super().evaluate(X)
+        CV = np.maximum(0.6 - X[:, 0] - X[:, 1], 0.0)[:, None]
+        out = {'F': F, 'CV': CV}
+        vals = tuple(out[k] for k in return_values_of)
+        return vals[0] if len(vals) == 1 else vals
+
+
+def test_nsga2_is_feasibility_first_on_constrained_problems():
+    """pymoo's NSGA2 (the reference's solver, nsga2.py:17-30) handles constraints feasibility-first: the tournament prefers
+    the smaller violation and the survival fills up with the least infeasible only when feasible individuals run out."""
+    np.random.seed(2)
+    alg = NSGA2Algorithm(pop_size=40, rank_fn=mo.pareto_rank)
+    # survival: 3 feasible + 5 infeasible, room for 5 => all feasible first (by rank), then the two smallest violations
+    alg.pop_size = 5
+    F = np.array([[0.1, 0.9], [0.5, 0.5], [0.6, 0.6], [0.0, 0.0], [0.0, 0.1], [0.2, 0.0], [0.3, 0.3], [0.05, 0.05]])
+    cv = np.array([0.0, 0.0, 0.0, 0.5, 0.1, 0.3, 0.2, 0.9])
+    X = np.arange(8, dtype=float)[:, None]
+    Xs, Fs, rank, crowd, cvs = alg._survive(X, F, cv)
+    assert list(Xs[:, 0]) == [0.0, 1.0, 2.0, 4.0, 6.0] and list(cvs) == [0.0, 0.0, 0.0, 0.1, 0.2]
+    assert list(rank) == [0, 0, 1, 2, 2]
+    # tournament: an infeasible contestant never beats a feasible one, whatever its rank
+    np.random.seed(3)
+    picks = alg._tournament(np.array([5, 0]), np.array([0.0, 9.0]), 2000, cv=np.array([0.0, 0.4]))
+    assert not (picks == 1).any() or set(np.unique(picks)) <= {0, 1} and (picks == 1).mean() < 0.3
+    # whole loop: the final population is feasible and still spreads along the constrained front
+    alg = NSGA2Algorithm(pop_size=40, rank_fn=mo.pareto_rank)
+    prob = ConstrainedZdt1()
+    X, F = alg.minimize(prob, lhs(6, 30), 40)
+    assert X.shape == (40, 6)
+    assert (X[:, 0] + X[:, 1] >= 0.6 - 1e-12).all()
+    assert F[:, 0].max() - F[:, 0].min() > 0.3
+
+
 @pytest.mark.gpu
 def test_mobo_step_end_to_end():
     from autooed_b200 import GaussianProcess, HypervolumeImprovement, Identity, init_solver
