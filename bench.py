@@ -253,6 +253,18 @@ def run_ours(args):
 
     # numerics guard: device leg and host leg agree (different chunk sizes => different partial-sum splits, not bitwise)
     same = bool(np.allclose(dA.cpu().numpy(), F, rtol=1e-11, atol=1e-12))
+    del F, dF
+
+    extras = {}
+    if args.extras != "none":
+        ctxt = dict(torch=torch, dist=dist, world=world, rank=rank, local=local, dev=dev, barrier=barrier, args=args)
+        extras.update(extra_fit_c4(gp_model=(X, Y), **ctxt))
+        if world > 1:
+            extras.update(extra_sharded_eval(gp, dX, **ctxt))
+        extras.update(extra_c5(**ctxt))
+        if rank == 0:
+            extras.update(extra_mobo())
+        barrier()
 
     if rank == 0:
         # ---- roofline of the dominant kernel (triangular FP64 DMMA product), timed with events per launch -------
@@ -276,8 +288,13 @@ def run_ours(args):
             if ks:
                 traffic = sum(k["dram_traffic_bytes"] for k in ks) / len(ks)
                 traffic_src = "profiles/ncu_trmm_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, mean of the LOWER and UPPER launch)"
+        issue_peak = None
+        probe = os.path.join(ROOT, "profiles", "fp64_pipe_probe_r01.json")
+        if os.path.exists(probe):  # DMMA issue-rate peak measured by tools/fp64_peaks.cu on this pool's B200 (no memory traffic)
+            issue_peak = json.load(open(probe)).get("dmma884_w32_tflops")
         roofline = {"bound": "tensor", "kernel": kname,
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_dmma_issue": issue_peak, "frac_of_dmma_issue_peak": (achieved / issue_peak) if issue_peak else None,
                     "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": 8.0 * m * (0.5 * N * N + 2.0 * N * min(C, 16384)),
                     "peak_source": "cuBLAS DGEMM fp64 8192^3 measured live in this run (MEASURED_PEAKS.json holds HBM and bf16 "
@@ -291,19 +308,212 @@ def run_ours(args):
         e2e_value = total / (ms_e2e * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": dict(w, candidates_per_gpu=C, parallelism=f"candidate-shard x{world}"),
+                "dtype": "f64", "data": "synthetic", "config": dict(w, candidates_per_gpu=C),
+                "parallelism": f"candidate-shard x{world}",
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": C * d * 8,
                         "d2h_bytes_per_step": C * m * (1 + d) * 8},
                 "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": blas_threads()[1], "kind": "port",
                                  "sample": f"{cpu_done} candidates of the same workload in {cpu_el:.1f}s (oracle/gp_oracle.py, numpy BLAS threads unrestricted)"},
                 "clocks": clocks, "device_host_legs_agree": same}
+        line.update(extras)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
+
+
+# =====================================================================================================================
+# extra keys of the contract line (outside its timed region): the configurations BASELINE.json names beside c4's evaluate
+# =====================================================================================================================
+def _max_over_ranks(torch, dist, world, dev, vals):
+    if world == 1:
+        return list(vals)
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def extra_fit_c4(gp_model, torch, dist, world, rank, local, dev, barrier, args):
+    """BASELINE config c4, the fit half: N=2000, d=20, m=3, 16 L-BFGS-B starts per objective (start 0 = theta0 of
+    gp.py:126-132, 15 log-uniform restarts, sklearn `n_restarts_optimizer` semantics), all 48 runs in lock-step on the
+    blocked factorisation.  Checked against the CPU oracle AT the optimum: same LML value, and the optimum is one of the
+    oracle's function too (projected gradient of -LML within L-BFGS-B's stopping tolerances).  With WORLD_SIZE > 1 the
+    same problems are then fitted with `fit_sharded` (6 problems per GPU at 8) and must give the same thetas."""
+    from autooed_b200 import GaussianProcess
+    from autooed_b200.problem import SimpleProblem
+    from autooed_b200.sharding import fit_sharded
+    from oracle import gp_oracle as go
+    X, Y = gp_model
+    N, d = X.shape
+    m = Y.shape[1]
+    out = {}
+    thetas_single = None
+    if rank == 0:
+        gp = GaussianProcess(SimpleProblem(d, m), nu=5, n_restarts=15, seed=3, device=local)
+        Yn = (Y - Y.mean(0)) / Y.std(0)
+        gp._set_train(X, Yn)
+        th0 = np.tile(go.initial_theta(d), (48, 1))
+        gp.log_marginal_likelihood_batch(np.arange(48) % m, th0, True)  # allocates the scratch of the blocked path
+        t0 = time.perf_counter()
+        gp.fit(X, Y)
+        wall = time.perf_counter() - t0
+        thetas_single = np.stack([g.kernel_.theta for g in gp.gps])
+        lml_star = [float(g.log_marginal_likelihood_value_) for g in gp.gps]
+        info = dict(gp.fit_info)
+        ctx, threads = blas_threads()
+        lo, hi = go.theta_bounds(d).T
+        rel, pg = [], []
+        with ctx:
+            t0 = time.perf_counter()
+            for o in range(m):
+                v, g = go.lml_and_grad(thetas_single[o], gp._Xn, gp._Yn[:, o], 5)
+                rel.append(abs(v - lml_star[o]) / abs(v))
+                g = -g  # gradient of the minimised -LML; projected onto the box (scipy's `pg` of L-BFGS-B)
+                proj = np.where((thetas_single[o] <= lo) & (g > 0), 0.0, np.where((thetas_single[o] >= hi) & (g < 0), 0.0, g))
+                pg.append(float(np.abs(proj).max()))
+            cpu_s = (time.perf_counter() - t0) / m
+        out["fit_c4"] = {"what": "full fit, N=2000 d=20 m=3, 16 starts per objective, 48 L-BFGS-B runs in lock-step",
+                         "wall_s": wall, "n_problems": info["n_problems"], "n_batches": info["n_batches"],
+                         "n_lml_evals": info["n_lml_evals"], "ms_per_lml_eval": 1e3 * wall / max(info["n_lml_evals"], 1),
+                         "lml_star": lml_star, "oracle_lml_rel_err_at_theta_star": rel, "oracle_lml_tol": 1e-6,
+                         "oracle_projected_gradient_inf_norm": pg,
+                         "relative_projected_gradient": [p / max(1.0, abs(v)) for p, v in zip(pg, lml_star)],
+                         "parity_ok": bool(max(rel) <= 1e-6),
+                         "cpu_port_s_per_lml_eval": cpu_s, "cpu_threads": threads,
+                         "cpu_port_s_extrapolated_same_evals": cpu_s * info["n_lml_evals"]}
+        del gp
+    if world > 1:
+        barrier()
+        gp2 = GaussianProcess(SimpleProblem(d, m), nu=5, n_restarts=15, seed=3, device=local)
+        t0 = time.perf_counter()
+        fit_sharded(gp2, X, Y)
+        torch.cuda.synchronize()
+        (wall_sh,) = _max_over_ranks(torch, dist, world, dev, [time.perf_counter() - t0])
+        if rank == 0:
+            th2 = np.stack([g.kernel_.theta for g in gp2.gps])
+            out["fit_sharded_s"] = wall_sh
+            out["fit_sharded"] = {"problems_per_rank": gp2.fit_info["n_problems_local"], "world": world,
+                                  "thetas_equal_single_rank_bitwise": bool(np.array_equal(th2, thetas_single)),
+                                  "max_abs_theta_diff": float(np.abs(th2 - thetas_single).max()),
+                                  "collectives": "broadcast_object_list(starts) + all_reduce(MIN) of 48 x (p+2) records"}
+        del gp2
+    return out
+
+
+def extra_sharded_eval(gp, dX_local, torch, dist, world, rank, local, dev, barrier, args):
+    """SURVEY.md §8(e) row 1 with the collective in the timed region: ONE fixed set of 2^20 candidates (strong scaling),
+    each rank evaluates its contiguous shard on the device and the results are all-gathered over NVLink
+    (`all_gather_into_tensor`, 25 MB of values + 503 MB of gradients).  Rank 0 re-evaluates one 16384-row chunk of the LAST
+    rank's shard alone and compares it with the gathered rows bit for bit."""
+    from autooed_b200 import _lib
+    from autooed_b200.sharding import evaluate_sharded_device, shard_bounds
+    N, d, m = gp._Xn.shape[0], gp.n_var, gp.n_obj
+    C = 1 << 20
+    Xs = candidates(C, d, 99)  # the same set on every rank
+    dX = torch.from_numpy(Xs).to(dev)
+    outbuf = None
+    A = dA = None
+    best = None
+    for rep in range(3):  # first repetition warms NCCL's communicator up
+        barrier()
+        t0 = time.perf_counter()
+        A, dA, tm = evaluate_sharded_device(gp, dX, C, _lib.ACQ_UCB, [float(N)], gradient=True, out=outbuf)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        outbuf = (A, dA) if A.shape[0] == C else None
+        vals = _max_over_ranks(torch, dist, world, dev, [tm["compute_ms"], tm["gather_ms"], tm["compute_ms"] + tm["gather_ms"], 1e3 * wall])
+        if rep > 0 and (best is None or vals[2] < best[2]):
+            best = vals
+    res = {}
+    if rank == 0:
+        lo, hi = shard_bounds(C, world, world - 1)
+        rows = min(16384, hi - lo)
+        a1 = torch.empty((rows, m), dtype=torch.float64, device=dev)
+        da1 = torch.empty((rows, m, d), dtype=torch.float64, device=dev)
+        gp.evaluate_device(dX[lo:lo + rows], rows, std=True, gradient=True, acq_kind=_lib.ACQ_UCB, acq_param=[float(N)], d_A=a1,
+                           d_dA=da1, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        eq = bool(torch.equal(a1, A[lo:lo + rows]) and torch.equal(da1, dA[lo:lo + rows]))
+        res = {"sharded_equals_single": eq, "gather_ms": best[1],
+               "sharded_eval": {"what": "strong scaling: 2^20 candidates in total, shards evaluated on the device, results all-gathered",
+                                "candidates_total": C, "compute_ms": best[0], "gather_ms": best[1], "total_ms": best[2],
+                                "wall_ms": best[3], "gathered_bytes": C * m * (1 + d) * 8,
+                                "value_evals_per_s": C / (best[2] * 1e-3), "rows_compared_bitwise": rows,
+                                "collective": "2 x ncclAllGather (in place) per call"}}
+    del dX, A, dA
+    return res
+
+
+def extra_c5(torch, dist, world, rank, local, dev, barrier, args):
+    """BASELINE config c5 per GPU: N=4000, d=32, m=3, UCB value + gradient over 2^20 candidates per GPU (8 M at 8 GPUs),
+    device-resident, one timed step after a short warm-up, max over ranks."""
+    from autooed_b200 import GaussianProcess, _lib
+    from autooed_b200.problem import SimpleProblem
+    w = WORKLOADS["c5"]
+    N, d, m, C = w["n_train"], w["n_var"], w["n_obj"], w["candidates_per_gpu"]
+    X, Y, thetas = make_problem(N, d, m)
+    gp = GaussianProcess(SimpleProblem(d, m), nu=w["nu"], device=local)
+    gp.fit_fixed(X, Y, thetas)
+    dX = torch.from_numpy(candidates(C, d, 2 + rank)).to(dev)
+    dA = torch.empty((C, m), dtype=torch.float64, device=dev)
+    ddA = torch.empty((C, m, d), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(rows):
+        gp.evaluate_device(dX, rows, std=True, gradient=True, acq_kind=_lib.ACQ_UCB, acq_param=[float(N)], d_A=dA, d_dA=ddA,
+                           stream=stream)
+
+    step(1 << 16)
+    step(1 << 16)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    step(C)
+    e1.record()
+    barrier()
+    (ms,) = _max_over_ranks(torch, dist, world, dev, [e0.elapsed_time(e1)])
+    del gp, dX, dA, ddA
+    torch.cuda.empty_cache()
+    return {"c5_value": C * world / (ms * 1e-3),
+            "c5": {"workload": w["workload"], "n_gpus": world, "ms_per_step": ms, "steps": 1, "candidates_total": C * world,
+                   "unit": UNIT}}
+
+
+def extra_mobo():
+    """MOBO iteration wall time (the second half of BASELINE.json's metric) on c1 (ZDT1 d=6 m=2, identity, NSGA-II pop 200
+    x 200 generations, batch 10) and c2 (DTLZ2 d=10 m=3, EI, pop 1000, batch 20): fit + solve + HVI select per iteration
+    on the B200 path, averaged over the iterations after the first (which pays allocations)."""
+    import random
+    from autooed_b200 import ExpectedImprovement, GaussianProcess, HypervolumeImprovement, Identity
+    from autooed_b200.mobo import MOBO
+    from autooed_b200.problem import SimpleProblem
+    from autooed_b200.solver import NSGA2
+    from autooed_b200.solver.nsga2 import lhs
+    out = {}
+    detail = {}
+    for name, f, d, m, acq_cls, pop, batch, n_init, iters in (("c1", _zdt1, 6, 2, Identity, 200, 10, 20, 8),
+                                                             ("c2", lambda X: _dtlz2(X, 3), 10, 3, ExpectedImprovement, 1000, 20, 30, 5)):
+        np.random.seed(0)
+        random.seed(0)
+        prob = SimpleProblem(d, m)
+        X = lhs(d, n_init)
+        Y = f(X)
+        sur = GaussianProcess(prob, nu=1)
+        opt = MOBO(prob, sur, acq_cls(sur), NSGA2(prob, n_gen=200, pop_size=pop), HypervolumeImprovement(sur))
+        times = []
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            Xn = opt.optimize(X, Y, None, batch)
+            times.append(time.perf_counter() - t0)
+            X, Y = np.vstack([X, Xn]), np.vstack([Y, f(Xn)])
+        out[f"mobo_{name}_s"] = float(np.mean(times[2:]))  # the first two iterations load kernels / build the CUDA graph
+        detail[name] = {"iterations_timed": iters - 2, "s_each": [round(t, 5) for t in times], "n_train_last": int(len(X) - batch)}
+    out["mobo"] = dict(detail, what="s per MOBO iteration (fit + 200 NSGA-II generations + HVI batch selection), B200 path; the "
+                                    "CPU arm with identical iterations is `bench.py --mode mobo`")
+    return out
 
 
 # =====================================================================================================================
@@ -638,6 +848,9 @@ def main():
     ap.add_argument("--mode", default="evals", choices=["evals", "fit", "mobo", "discovery"],
                     help="evals = the contract line (default); fit / mobo = secondary measurements, one JSON line each")
     ap.add_argument("--mobo-iters", type=int, default=20)
+    ap.add_argument("--extras", default="all", choices=["all", "none"],
+                    help="all = also run the full c4 fit, the c5 shape, the sharded (gathered) legs at N > 1 and the MOBO "
+                         "iterations, reported as extra keys of the one JSON line; none = the contract legs only")
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS),
                     help="c4 = the configuration the metric is quoted on (default); c5 = the N=4000, d=32 sharding-sweep shape")
     args = ap.parse_args()
