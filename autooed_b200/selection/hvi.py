@@ -1,7 +1,9 @@
 """Hypervolume-improvement selection — drop-in for `autooed/mobo/selection/hvi.py:16-47`.
-The batch x |candidates| exact-hypervolume loop of the reference runs as greedy rounds of one kernel
-(`aoed_hvi_select`); only the random fallback (hvi.py:38-39) stays on the host because it consumes the
-global numpy RNG."""
+The batch x |candidates| exact-hypervolume loop of the reference runs as device-resident greedy rounds (`aoed_hvi_select`:
+one kernel per round, candidates / front / taken mask stay on the GPU, no host synchronisation between rounds); a near-tie
+between the two best candidates of a round is re-decided inside the library with the reference's own
+`HV(front + y) - HV(front)` form (hvi.py:28-37); only the random fallback (hvi.py:38-39) stays here because it consumes
+the global numpy RNG."""
 import numpy as np
 
 from autooed_b200 import _lib
@@ -43,5 +45,5 @@ class HypervolumeImprovement(Selection):
     Selection based on Hypervolume improvement.
     '''
     def _select(self, X_candidate, Y_candidate, X, Y, batch_size):
-        idx = hvi_select_indices(Y_candidate, Y, batch_size)
+        idx = hvi_select_indices(Y_candidate, Y, batch_size, device=getattr(self.surrogate_model, 'device', 0))
         return X_candidate[idx]

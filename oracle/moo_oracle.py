@@ -86,12 +86,17 @@ def _hv_boxes(Q):
 
 
 def hypervolume(F, ref_point):
-    """pymoo 0.4.1 `Hypervolume(ref_point=r).calc(F)` for minimisation: points with any coordinate
-    above r are discarded, the rest is measured against r."""
+    """pymoo 0.4.1 `Hypervolume(ref_point=r).calc(F)` for minimisation: `_calc` keeps only the
+    first non-dominated front of F (`NonDominatedSorting().do(F, only_non_dominated_front=True)`, rows in their
+    original order; equal rows do not dominate each other), the vendored indicator then discards points with any
+    coordinate above r and measures the rest against r.  The pre-filter is what makes HV(P + y) - HV(P) EXACTLY zero
+    for a candidate y that a front point weakly dominates."""
     F = np.atleast_2d(np.asarray(F, dtype=np.float64))
     ref = np.asarray(ref_point, dtype=np.float64)
     if F.size == 0:
         return 0.0
+    dom = np.logical_and((F[:, None, :] <= F[None, :, :]).all(2), (F[:, None, :] < F[None, :, :]).any(2))  # [j, i]: j dom i
+    F = F[~dom.any(axis=0)]
     F = F[(F <= ref).all(axis=1)]
     if len(F) == 0:
         return 0.0

@@ -100,6 +100,105 @@ def test_hvi_select_same_batch(m, C, N, batch):
     assert list(got) == want
 
 
+def _nudge(y, rng, ulps=1):
+    y = y.copy()
+    k = rng.integers(len(y))
+    for _ in range(ulps):
+        y[k] = np.nextafter(y[k], rng.choice([-np.inf, np.inf]))
+    return y
+
+
+@pytest.mark.parametrize("m", [2, 3])
+def test_hvi_exact_ties_and_one_ulp_near_ties(m):
+    """Candidates whose contributions coincide exactly (duplicates, mirror images) or differ in the last place: the
+    reference decides them by rounding of HV(front + y) - HV(front) with a strict '>' in index order (hvi.py:33-37).
+    The library re-decides such rounds on the host in that very form, so the batch equals the oracle's (which evaluates
+    the difference form literally) in every instance."""
+    from autooed_b200.selection.hvi import hvi_select_indices
+    rng = np.random.default_rng(40 + m)
+    for inst in range(25):
+        Y = rng.random((25, m)) * 0.6 + 0.35
+        base = rng.random((12, m)) * 0.7
+        rows = [base]
+        rows.append(np.stack([_nudge(b, rng, ulps=int(rng.integers(1, 3))) for b in base]))  # 1-2 ulp neighbours
+        rows.append(base[:4].copy())                                                            # exact duplicates
+        if m == 2:
+            rows.append(base[:4, ::-1].copy())                                                  # mirror images
+        Yc = np.vstack(rows)
+        Yc = Yc[rng.permutation(len(Yc))]
+        np.random.seed(inst)
+        want = mo.hvi_select(Yc, Y, 6)
+        np.random.seed(inst)
+        got = hvi_select_indices(Yc, Y, 6)
+        assert list(got) == want, (inst, list(got), want)
+
+
+def test_hvi_tie_guard_changes_nothing_without_ties(monkeypatch):
+    """Generic candidates: the device-resident loop alone (guard off) and the guarded call agree with the oracle."""
+    from autooed_b200.selection.hvi import hvi_select_indices
+    rng = np.random.default_rng(9)
+    Y = rng.random((50, 3)) + 0.2
+    Yc = rng.random((800, 3))
+    np.random.seed(1)
+    want = mo.hvi_select(Yc, Y, 8)
+    np.random.seed(1)
+    assert list(hvi_select_indices(Yc, Y, 8)) == want
+
+
+@pytest.mark.parametrize("m,C,batch", [(2, 100000, 12), (3, 100000, 8)])
+def test_hvi_device_loop_at_1e5_candidates(m, C, batch):
+    """10^5 candidates: every round of the device-resident loop equals an independent evaluation of that round (the
+    one-shot contribution kernel + numpy arg-max, first maximum), and the winning contributions equal the oracle's
+    HV(front + y) - HV(front) for the winner and for a sample of other candidates."""
+    from autooed_b200 import _lib
+    from autooed_b200.utils import pareto
+    rng = np.random.default_rng(m)
+    Y = rng.random((200, m)) * 0.5 + 0.5
+    Yc = rng.random((C, m)) ** 0.5
+    front0 = pareto.find_pareto_front(Y)
+    ref = np.max(np.vstack([Yc, Y]), axis=0)
+    idx = np.full(batch, -1, dtype=np.int64)
+    con = np.zeros(batch)
+    _lib.check(_lib.load().aoed_hvi_select(0, C, m, _lib.ptr(_lib.as_f64(Yc)), len(front0), _lib.ptr(_lib.as_f64(front0)),
+                                           _lib.ptr(_lib.as_f64(ref)), batch, None, _lib.ptr(idx), _lib.ptr(con)))
+    assert (idx >= 0).all() and len(set(idx)) == batch
+    front, free = front0.copy(), np.ones(C, dtype=bool)
+    for r in range(batch):
+        c = np.where(free, pareto.hv_contributions(Yc, front, ref), 0.0)
+        j = int(np.argmax(c))
+        assert j == idx[r] and c[j] == con[r]
+        if r % 3 == 0:
+            probe = np.concatenate([[j], rng.choice(C, 20, replace=False)])
+            want = mo.hv_contributions_by_difference(Yc[probe], front, ref)
+            assert np.allclose(c[probe] * free[probe], want * free[probe], rtol=1e-9, atol=1e-13)
+        free[j] = False
+        front = np.vstack([front, Yc[j]])
+
+
+@pytest.mark.parametrize("n,m", [(20000, 2), (50000, 3), (30000, 4)])
+def test_pareto_filter_path_equals_direct_path(n, m, monkeypatch):
+    """Above 16384 rows the mask comes from the sample-skyline filter (O(n |S0| + |R|^2)); it must equal the all-pairs
+    pass bit for bit, with ties and duplicates, and on a row shard."""
+    from autooed_b200 import _lib
+    from autooed_b200.utils import pareto
+    rng = np.random.default_rng(n + m)
+    Y = rng.random((n, m))
+    Y[n // 2:] = np.round(Y[n // 2:], 2)
+    Y[:100] = Y[100:200]
+    monkeypatch.setenv("AOED_PARETO_PATH", "direct")
+    direct = pareto.check_pareto(Y)
+    monkeypatch.setenv("AOED_PARETO_PATH", "filter")
+    filt = pareto.check_pareto(Y)
+    assert np.array_equal(direct, filt) and direct.sum() > 0
+    lo, hi = n // 3, n // 3 + 5000
+    out = np.zeros(hi - lo, dtype=np.uint8)
+    _lib.check(_lib.load().aoed_pareto_mask_rows(0, n, m, _lib.ptr(_lib.as_f64(Y)), lo, hi, _lib.ptr(out)))
+    assert np.array_equal(out.astype(bool), direct[lo:hi])
+    # and the small fixtures through the filter path
+    Ys = np.round(rng.random((300, m)), 1)
+    assert np.array_equal(pareto.check_pareto(Ys), mo.check_pareto(Ys))
+
+
 def test_hvi_random_fallback_same_seed():
     """All candidates dominated by the data: every pick is the reference's np.random.choice (hvi.py:38-39)."""
     from autooed_b200.selection.hvi import hvi_select_indices
