@@ -351,6 +351,8 @@ __global__ void __launch_bounds__(HVI_THREADS) hvi_round_kernel(HviArgs a) {
             } else {
                 v = Excl<M, M>::run(y, sfront, k, sref, lev);
             }
+            // contributions only shrink as the front grows: a candidate at zero stays at zero and is skipped from now on
+            if (!(v > 0.0)) a.excluded[i] = 2;
         }
         top_push(t, v, i);
     }
@@ -837,15 +839,9 @@ int aoed_hvi_select(int device, int64_t n_cand, int m, const double* h_Yc, int64
     std::vector<double> front(h_front, h_front + size_t(n_front) * m);
     std::vector<uint8_t> taken(size_t(n_cand), 0);
     if (h_excluded) taken.assign(h_excluded, h_excluded + n_cand);
-    double box = 1.0;  // volume of the reference box: cheap upper bound of any hypervolume below
-    {
-        std::vector<double> lo(h_ref, h_ref + m);
-        for (size_t i = 0; i < front.size() / m; ++i)
-            for (int t = 0; t < m; ++t) lo[t] = std::min(lo[t], front[i * m + t]);
-        for (int64_t i = 0; i < n_cand; ++i)
-            for (int t = 0; t < m; ++t) lo[t] = std::min(lo[t], h_Yc[i * m + t]);
-        for (int t = 0; t < m; ++t) box *= std::max(h_ref[t] - lo[t], 0.0);
-    }
+    // running hypervolume of the front: HV(front_0) once, then every accepted winner adds exactly its contribution — the scale
+    // against which a gap between the two best candidates counts as a near-tie
+    double hv_run = host_hypervolume(front, nullptr, m, h_ref);
     constexpr double kTieRel = 1e-12;
     static const bool no_guard = getenv("AOED_HVI_TIE_GUARD") && getenv("AOED_HVI_TIE_GUARD")[0] == '0';
     std::vector<double> v1(batch), v2(batch), contrib;
@@ -878,9 +874,9 @@ int aoed_hvi_select(int device, int64_t n_cand, int m, const double* h_Yc, int64
             long long win = i1[r];
             double win_v = v1[r];
             const double gap = v1[r] - std::max(v2[r], 0.0);
-            if (!no_guard && gap <= kTieRel * (box + v1[r])) {
+            if (!no_guard && gap <= kTieRel * (hv_run + v1[r])) {
                 const double hv0 = host_hypervolume(front, nullptr, m, h_ref);
-                if (gap <= kTieRel * (hv0 + v1[r])) {
+                {
                     // every candidate within the tolerance of the best takes part; HV(P u {y}) - HV(P) with strict '>' in
                     // index order (hvi.py:27-37)
                     std::vector<double> fsr = sort_front(front.data(), int64_t(front.size() / m), m);
@@ -910,6 +906,7 @@ int aoed_hvi_select(int device, int64_t n_cand, int m, const double* h_Yc, int64
                     restart = true;  // the device state was overwritten for the re-decision (and may have followed another winner)
                 }
             }
+            hv_run += win_v;
             h_idx[done] = win;
             if (h_contrib) h_contrib[done] = win_v;
             taken[size_t(win)] = 1;
