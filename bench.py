@@ -798,6 +798,21 @@ def run_discovery_mode(args):
         calls["rows"] += len(np.atleast_2d(x))
         return sp.evaluate(x, return_values_of=return_values_of)
 
+    # ---- BASELINE config c3 end to end: the ParetoDiscovery solver (pop 100 x 10 generations) proposing a batch of 10 ----
+    from autooed_b200 import init_solver
+    solver = init_solver('discovery', {'n_gen': 10, 'pop_size': pop}, prob)
+    np.random.seed(1)
+    t0 = time.perf_counter()
+    Xc, Yc = solver.solve(X, Y, 10, acq)
+    dt = time.perf_counter() - t0
+    algo = solver.algo
+    print(json.dumps({"mode": "discovery", "arm": "b200", "what": "c3 end to end: ParetoDiscovery solver, ZDT3 d=10, GP nu=5/2 + identity, "
+                      "pop 100 x 10 generations, batch 10 (buffer + stochastic sampling + batched inner loop + family proposal)",
+                      "s_total": dt, "s_per_generation": dt / 10, "surrogate_rows_evaluated": int(solver.n_eval),
+                      "buffer_samples": int(algo.buffer.sample_count), "families": int(len(set(int(l) for l in algo.fam_lbls))),
+                      "approx_front_size": int(len(algo.approx_front)), "proposed": [int(Xc.shape[0]), int(Xc.shape[1])],
+                      "sparse_approximation": "unary-only fallback (pygco absent)"}), flush=True)
+
     xs = rng.random((pop, d))
     bounds = np.stack([np.zeros(d), np.ones(d)])
     origin = Y.min(axis=0)
