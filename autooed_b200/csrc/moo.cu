@@ -870,7 +870,41 @@ int aoed_hvi_select(int device, int64_t n_cand, int m, const double* h_Yc, int64
         // ---- validate round by round: a near-tie between the two best is re-decided in the reference's form ----
         bool restart = false;
         for (int r = 0; r < st.round && !restart; ++r) {
-            if (i1[r] < 0) return AOED_OK;  // no positive contribution: the caller draws the random pick (hvi.py:38-39)
+            if (i1[r] < 0) {
+                // No positive exclusive volume.  In the reference's form a candidate that no front point weakly dominates
+                // can still come out positive by rounding of the two hypervolumes (e.g. one that defines the reference
+                // point: zero-volume box, but it survives pymoo's non-dominated pre-filter and perturbs the summation);
+                // weakly dominated ones give exactly zero.  Evaluate those few in that form before giving up.
+                const double hv0 = host_hypervolume(front, nullptr, m, h_ref);
+                const size_t kf = front.size() / m;
+                double best = 0.0;
+                long long best_i = -1;
+                for (int64_t c = 0; c < n_cand; ++c) {
+                    if (taken[c]) continue;
+                    const double* y = h_Yc + c * m;
+                    bool covered = false;
+                    for (size_t f = 0; f < kf && !covered; ++f) {
+                        bool le = true;
+                        for (int t = 0; t < m; ++t) le = le && (front[f * m + t] <= y[t]);
+                        covered = le;
+                    }
+                    if (covered) continue;
+                    const double d = host_hypervolume(front, y, m, h_ref) - hv0;
+                    if (d > best) {
+                        best = d;
+                        best_i = c;
+                    }
+                }
+                if (best_i < 0) return AOED_OK;  // the caller draws the random pick (hvi.py:38-39)
+                hv_run += best;
+                h_idx[done] = best_i;
+                if (h_contrib) h_contrib[done] = best;
+                taken[size_t(best_i)] = 1;
+                for (int t = 0; t < m; ++t) front.push_back(h_Yc[best_i * m + t]);
+                ++done;
+                restart = true;
+                break;
+            }
             long long win = i1[r];
             double win_v = v1[r];
             const double gap = v1[r] - std::max(v2[r], 0.0);

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — pins the ParetoDiscovery shell (performance buffer insert / move_origin /
 _update_cell / sample / flattened, stochastic sampling, family-aware batch proposal) to the reference: runs the UNMODIFIED
 `/root/reference/autooed/mobo/solver/pareto_discovery/buffer.py:10-183,306-398`, `pareto_discovery.py:529-560` and
-`utils.py:5-134` on seeded inputs and writes `tests/golden/discovery_buffer.npz`.
+`utils.py:5-134` on seeded inputs and writes `tests/golden/pdshell_cases.npz`.
 
 pygco / pymoo are absent: `pygco.cut_from_graph` is only reached by `sparse_approximation` (not recorded), and
 `pymoo.factory.get_performance_indicator('hv', ref_point=r)` is stood in by the oracle's exact hypervolume (so the LOOP
@@ -118,8 +118,8 @@ def main():
         rec.update({f"{tag}_front": front, f"{tag}_pf": pf, f"{tag}_ps": ps, f"{tag}_labels": labels, f"{tag}_ref": ref,
                     f"{tag}_batch": np.int64(batch), f"{tag}_X": Xn, f"{tag}_Y": Yn, f"{tag}_fam": np.array(fam),
                     f"{tag}_X_nolabel": Xn2, f"{tag}_Y_nolabel": Yn2})
-    np.savez_compressed(os.path.join(OUT, "discovery_buffer.npz"), **rec)
-    print("wrote discovery_buffer.npz with", len(rec), "arrays")
+    np.savez_compressed(os.path.join(OUT, "pdshell_cases.npz"), **rec)
+    print("wrote pdshell_cases.npz with", len(rec), "arrays")
 
 
 if __name__ == "__main__":

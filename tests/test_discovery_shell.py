@@ -1,5 +1,5 @@
 """The ParetoDiscovery shell around the batched inner loop against fixtures generated from the
-UNMODIFIED reference (`oracle/make_golden_buffer.py` -> tests/golden/discovery_buffer.npz): performance buffer
+UNMODIFIED reference (`oracle/make_golden_buffer.py` -> tests/golden/pdshell_cases.npz): performance buffer
 (`buffer.py:10-183, 306-398`), stochastic sampling (`pareto_discovery.py:529-560`), family-aware batch proposal
 (`utils.py:5-134`).  Buffer and sampling are host logic (CPU tests); the proposal loop runs its hypervolume rounds on the
 GPU and the solver class runs BASELINE config c3 end to end."""
@@ -12,7 +12,7 @@ from conftest import GOLDEN
 from autooed_b200.solver import discovery_buffer as db
 from autooed_b200.solver import pareto_discovery as pdis
 
-Z = dict(np.load(os.path.join(GOLDEN, "discovery_buffer.npz")))
+Z = dict(np.load(os.path.join(GOLDEN, "pdshell_cases.npz")))
 
 
 def _cells_equal(buf, key):
