@@ -438,6 +438,12 @@ int launch_trmm_tma(aoed_gp* gp, const CUtensorMap& mapA, const CUtensorMap& map
         ticket = gp->dTickets + gp->ticket_slot;
     }
     t.counter = ticket;
+    static const int col_group = [] {
+        const char* e = getenv("AOED_TRMM_COLGROUP");
+        const int v = e ? atoi(e) : PT_COL_GROUP;
+        return v >= 1 ? v : PT_COL_GROUP;
+    }();
+    t.colGroup = col_group;
     CU(cudaMemsetAsync(t.counter, 0, sizeof(int), s));
     static const bool debug = getenv("AOED_TRMM_DEBUG") != nullptr;
     if (debug && gp->hDbg == nullptr) {
@@ -770,6 +776,12 @@ int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu) {
     DeviceGuard guard_(device);
     CU(guard_.err);
     aoed_gp* gp = new aoed_gp();
+    struct Guard {  // a failure below must not leak the half-built handle (streams, events)
+        aoed_gp* h;
+        ~Guard() {
+            if (h) aoed_gp_destroy(h);
+        }
+    } guard{gp};
     gp->device = device; gp->d = n_var; gp->m = n_obj; gp->nu = nu; gp->DP = DP;
     query_occupancy(nu, DP, gp->occ_xcov, gp->occ_gradsum);
     gp->trmm_variant = trmm_variant_from_env();
@@ -784,6 +796,7 @@ int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu) {
     }
     CU(cudaEventCreate(&gp->ev0));
     CU(cudaEventCreate(&gp->ev1));
+    guard.h = nullptr;
     *out = gp;
     return AOED_OK;
 }
@@ -1223,6 +1236,14 @@ int aoed_gp_eval(aoed_gp_t* gp, int64_t n_rows, const double* h_Xn, uint32_t fla
     // triangular products of two chunks and lose ~4 % (measured).
     cudaStream_t sc = gp->streams[0], sh = gp->streams[1], sd = gp->d2h_stream;
     CU(cudaStreamSynchronize(sc));  // earlier device-API work on the compute stream's workspaces
+    struct DrainGuard {  // an error return below must not leave copies into the caller's (pooled, recyclable) buffers in flight
+        cudaStream_t a, b, c;
+        ~DrainGuard() {
+            cudaStreamSynchronize(a);
+            cudaStreamSynchronize(b);
+            cudaStreamSynchronize(c);
+        }
+    } drain{sh, sc, sd};
     int slot = 0;
     bool used[2] = {false, false};
     for (int64_t r0 = 0; r0 < n_rows; r0 += cap, slot = (slot + 1) % nslots) {

@@ -559,7 +559,7 @@ std::vector<double> sort_front(const double* front, int64_t k, int m) {
 
 // ---- host-side exact hypervolume in the reference's DIFFERENCE form (near-tie re-decision) --------------------------
 // Volume of the union of the boxes [0, q]: slicing along the last coordinate, the same sequence of floating-point
-// operations as the CPU oracle's restatement of pymoo's exact indicator, so that HV(P u {y}) - HV(P) (hvi.py:28-34)
+// operations as the test suite's CPU restatement of pymoo's exact indicator, so that HV(P u {y}) - HV(P) (hvi.py:28-34)
 // orders near-ties the way that formulation does.  volatile temporaries keep the compiler from contracting a*b+c.
 double hv_boxes(std::vector<const double*> q, int m) {
     const size_t k = q.size();

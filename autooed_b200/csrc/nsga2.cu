@@ -141,10 +141,10 @@ __global__ void __launch_bounds__(32 * DUP_WARPS) duplicate_kernel(const double*
                                                                    const double* __restrict__ Xoff, int P, int d,
                                                                    uint8_t* __restrict__ dup, unsigned long long* n_eval,
                                                                    int* gen) {
-    extern __shared__ double dup_key[];  // [n_cur + P]
+    extern __shared__ double dup_key[];  // [n_cur + P] first coordinates: a cheap necessary condition before the full distance
     if (blockIdx.x == 0 && threadIdx.x == 0) *gen += 1;  // the variation kernel of this generation has read it
     for (int j = threadIdx.x; j < n_cur + P; j += 32 * DUP_WARPS)
-        dup_key[j] = rint((j < n_cur ? Xpop[int64_t(j) * d] : Xoff[int64_t(j - n_cur) * d]) * 1e8);
+        dup_key[j] = j < n_cur ? Xpop[int64_t(j) * d] : Xoff[int64_t(j - n_cur) * d];
     __syncthreads();
     const int o = blockIdx.x * DUP_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (o >= P) return;
@@ -152,12 +152,16 @@ __global__ void __launch_bounds__(32 * DUP_WARPS) duplicate_kernel(const double*
     const double q0 = dup_key[n_cur + o];
     const int total = n_cur + o;
     bool same_any = false;
+    // pymoo DefaultDuplicateElimination: Euclidean distance to a population member or an EARLIER offspring <= 1e-16
     for (int j = lane; j < total; j += 32) {
-        if (dup_key[j] == q0) {  // rare: compare the other coordinates
+        if (fabs(dup_key[j] - q0) <= 1e-16) {  // rare: the full distance
             const double* x = j < n_cur ? Xpop + int64_t(j) * d : Xoff + int64_t(j - n_cur) * d;
-            bool same = true;
-            for (int k = 1; k < d && same; ++k) same = rint(x[k] * 1e8) == rint(xo[k] * 1e8);
-            same_any = same_any || same;
+            double d2 = 0.0;
+            for (int k = 0; k < d; ++k) {
+                const double t = x[k] - xo[k];
+                d2 = fma(t, t, d2);
+            }
+            same_any = same_any || (sqrt(d2) <= 1e-16);
         }
     }
     const bool found = __any_sync(0xffffffffu, same_any);
@@ -485,9 +489,11 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
         return AOED_OK;
     };
 
-    // generation 1 = evaluation of the given sampling, truncated only when it exceeds pop_size
+    // generation 1 = evaluation of the given sampling.  pymoo's `_initialize` runs the survival with
+    // n_survive = len(pop): the WHOLE sampling (ranked, with crowding distances) parents the first offspring, the cut to
+    // pop_size happens at the first merge
     NCHK(evaluate(bX[0].as<double>(), n_init, bF[0].as<double>()));
-    int n_cur = int(std::min<int64_t>(n_init, P));
+    int n_cur = int(n_init);
     NCHK(survive(0, int(n_init), nullptr, nullptr, nullptr, 0, n_cur, 1));
     int cur = 1;
     int64_t evals = n_init;
@@ -547,6 +553,7 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
     }
     for (; g < n_gen; ++g) NCHK(generation());
     const auto t_enqueued = std::chrono::steady_clock::now();
+    n_cur = std::min(n_cur, P);  // n_gen == 1 with a sampling larger than pop_size: the best pop_size rows (the output capacity)
     NCU(cudaMemcpyAsync(h_X, bX[cur].p, size_t(n_cur) * d * sizeof(double), cudaMemcpyDeviceToHost, s));
     NCU(cudaMemcpyAsync(h_F, bF[cur].p, size_t(n_cur) * m * sizeof(double), cudaMemcpyDeviceToHost, s));
     unsigned long long off_evals = 0;

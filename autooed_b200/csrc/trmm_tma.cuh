@@ -86,27 +86,28 @@ struct TrmmTmaArgs {
     int mTiles, colTiles, batch;
     int* counter;     // tile ticket counter, zeroed before the launch
     int* dbg;         // host-mapped diagnostics (who timed out where), or nullptr
+    int colGroup;     // column tiles whose B panels (all batches) are meant to stay L2-resident together
 };
 
-constexpr int PT_COL_GROUP = 8;  // column tiles whose B panels (all batches) are meant to stay L2-resident together
+constexpr int PT_COL_GROUP = 8;  // default colGroup (AOED_TRMM_COLGROUP overrides)
 
 // Ticket -> tile.  Order: groups of PT_COL_GROUP column tiles outermost (their B panels, 8*128 columns x Npad x batch
 // = 50 MB at N = 2048, m = 3, stay in the 126 MB L2 while every row tile of the group streams over them), inside a group
 // heaviest row tiles first, then batch, then column tile (CTAs running concurrently share the A panel of one row tile).
 template <bool UPPER>
-__device__ __forceinline__ void decode_tile(int t, int mTiles, int colTiles, int batch, int& mt, int& b, int& ct) {
-    const int full = PT_COL_GROUP * batch * mTiles;
-    const int ng = (colTiles + PT_COL_GROUP - 1) / PT_COL_GROUP;
-    int grp = t / full, r = t - grp * full, gsz = PT_COL_GROUP;
+__device__ __forceinline__ void decode_tile(int t, int mTiles, int colTiles, int batch, int colGroup, int& mt, int& b, int& ct) {
+    const int full = colGroup * batch * mTiles;
+    const int ng = (colTiles + colGroup - 1) / colGroup;
+    int grp = t / full, r = t - grp * full, gsz = colGroup;
     if (grp >= ng - 1) {
         grp = ng - 1;
         r = t - grp * full;
-        gsz = colTiles - grp * PT_COL_GROUP;
+        gsz = colTiles - grp * colGroup;
     }
     const int mr = r / (gsz * batch), rem = r - mr * (gsz * batch);
     mt = UPPER ? mr : mTiles - 1 - mr;
     b = rem / gsz;
-    ct = grp * PT_COL_GROUP + (rem - b * gsz);
+    ct = grp * colGroup + (rem - b * gsz);
 }
 
 template <bool UPPER>
@@ -145,7 +146,7 @@ trmm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 return;
             }
             int mt, b, ct;
-            decode_tile<UPPER>(tile, p.mTiles, p.colTiles, p.batch, mt, b, ct);
+            decode_tile<UPPER>(tile, p.mTiles, p.colTiles, p.batch, p.colGroup, mt, b, ct);
             const int k_begin = UPPER ? mt * TM : 0;
             const int k_end = UPPER ? p.Kpad : min(p.Kpad, (mt + 1) * TM);
             const int KT = (k_end - k_begin) / TK;
@@ -188,7 +189,7 @@ trmm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int tile = stage_tile[it % PT_STAGES];
         if (tile < 0) break;
         int mt, b, ct;
-        decode_tile<UPPER>(tile, p.mTiles, p.colTiles, p.batch, mt, b, ct);
+        decode_tile<UPPER>(tile, p.mTiles, p.colTiles, p.batch, p.colGroup, mt, b, ct);
         const int k_begin = UPPER ? mt * TM : 0;
         const int k_end = UPPER ? p.Kpad : min(p.Kpad, (mt + 1) * TM);
         const int KT = (k_end - k_begin) / TK;

@@ -2,7 +2,8 @@
 
 Reference: `autooed/mobo/solver/nsga2.py:13-30` delegates to pymoo 0.4.1 `NSGA2(pop_size)` + `minimize(..., ('n_gen', G))`.
 pymoo is not part of this repository, so the algorithm is written out here with pymoo 0.4.1's defaults (SURVEY.md
-Appendix F): the initial population is the given sampling as is; binary tournament on (rank, crowding distance);
+Appendix F): the initial population is the given sampling as is — all of it (ranked) parents the first offspring, the cut to
+pop_size happens at the first merge, as pymoo's `_initialize` runs its survival with n_survive = len(pop); binary tournament on (rank, crowding distance);
 simulated binary crossover (prob 0.9, eta 15, per-variable exchange prob 0.5); polynomial mutation (eta 20, prob
 1/n_var); duplicate elimination; n_offsprings = pop_size; rank-and-crowding survival; generation 1 is the evaluation of
 the initial population.  Populations are NOT seed-for-seed identical with pymoo (different RNG call order); every
@@ -96,19 +97,23 @@ class NSGA2Algorithm:
         return np.clip(np.where(do, X + dq * span, X), xl, xu)
 
     @staticmethod
-    def _drop_duplicates(X, others, resolution=1e-8):
-        """Offspring that coincide with a population member or an earlier offspring are discarded.  pymoo compares all
-        pairwise squared distances with 1e-16 (an O(n^2 d) matrix per generation — 80 % of the host time at pop 1000);
-        here rows are compared on the 1e-8 grid that threshold corresponds to, by hashing."""
-        def keys(A):
-            q = np.round(np.ascontiguousarray(A) / resolution).astype(np.int64)
-            return [row.tobytes() for row in q]
-        seen = set(keys(others)) if len(others) else set()
-        keep = np.zeros(len(X), dtype=bool)
-        for i, k in enumerate(keys(X)):
-            if k not in seen:
-                seen.add(k)
-                keep[i] = True
+    def _drop_duplicates(X, others, epsilon=1e-16):
+        """pymoo `DefaultDuplicateElimination`: an offspring is discarded when its Euclidean distance to a population
+        member, or to an EARLIER offspring, is <= 1e-16 (i.e. the same point).  Candidates for that are found on the first
+        coordinate (sorted search) so that the check stays far below the O(n^2 d) distance matrix at pop 1000."""
+        X = np.ascontiguousarray(X, dtype=float)
+        ref = np.vstack([others, X]) if len(others) else X
+        n0 = len(ref) - len(X)
+        order = np.argsort(ref[:, 0], kind='stable')
+        key = ref[order, 0]
+        lo = np.searchsorted(key, X[:, 0] - epsilon, side='left')
+        hi = np.searchsorted(key, X[:, 0] + epsilon, side='right')
+        keep = np.ones(len(X), dtype=bool)
+        for i in np.flatnonzero(hi - lo > 1):  # more than the point itself shares the first coordinate
+            cand = order[lo[i]:hi[i]]
+            cand = cand[cand < n0 + i]  # population members and earlier offspring only
+            if len(cand) and (np.sqrt(((ref[cand] - X[i]) ** 2).sum(axis=1)) <= epsilon).any():
+                keep[i] = False
         return X[keep]
 
     # -- survival --------------------------------------------------------------------------------------------------
@@ -120,14 +125,15 @@ class NSGA2Algorithm:
             crowd[idx] = crowding_distance(F[idx])
         return rank, crowd
 
-    def _survive(self, X, F, cv=None):
+    def _survive(self, X, F, cv=None, n_survive=None):
         """Rank-and-crowding survival.  With constraints (pymoo `Survival.do`, filter_infeasible=True): the feasible
         individuals compete by rank and crowding for the `pop_size` places; places left over go to the infeasible ones
         in order of increasing violation (they carry the rank after the last feasible front and zero crowding)."""
+        pop_size = self.pop_size if n_survive is None else n_survive
         if cv is None or not (cv > 0.0).any():
             rank, crowd = self._rank_and_crowding(F)
-            if len(X) > self.pop_size:
-                order = np.lexsort((-crowd, rank))[:self.pop_size]  # fronts in order, last front by crowding descending
+            if len(X) > pop_size:
+                order = np.lexsort((-crowd, rank))[:pop_size]  # fronts in order, last front by crowding descending
                 X, F, rank, crowd = X[order], F[order], rank[order], crowd[order]
                 cv = None if cv is None else cv[order]
             return X, F, rank, crowd, cv
@@ -135,9 +141,9 @@ class NSGA2Algorithm:
         keep, rank, crowd = np.empty(0, dtype=int), np.empty(0, dtype=int), np.empty(0)
         if len(feas):
             r, c = self._rank_and_crowding(F[feas])
-            order = np.lexsort((-c, r))[:self.pop_size]
+            order = np.lexsort((-c, r))[:pop_size]
             keep, rank, crowd = feas[order], r[order], c[order]
-        room = min(self.pop_size, len(X)) - len(keep)
+        room = min(pop_size, len(X)) - len(keep)
         if room > 0:
             worst = infeas[np.argsort(cv[infeas], kind='stable')[:room]]
             base = (rank.max() + 1) if len(rank) else 0
@@ -159,7 +165,8 @@ class NSGA2Algorithm:
         X = np.array(X0, dtype=float)
         F, cv = self._evaluate(problem, X, constrained)
         self.n_eval = len(X)
-        X, F, rank, crowd, cv = self._survive(X, F, cv)
+        # pymoo `_initialize`: survival with n_survive = len(pop) — the whole sampling parents the first offspring
+        X, F, rank, crowd, cv = self._survive(X, F, cv, n_survive=len(X))
         for _ in range(n_gen - 1):
             off = np.empty((0, X.shape[1]))
             for _attempt in range(10):  # refill after duplicate elimination, as pymoo's mating loop does

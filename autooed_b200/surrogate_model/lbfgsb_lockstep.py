@@ -10,7 +10,8 @@ small fits of a MOBO iteration).
 
 `setulb` is a private scipy interface, so `available()` first replays a small problem against `scipy.optimize.minimize`
 and compares x, f and the evaluation count exactly; any exception or difference sends the caller back to the threaded
-driver.
+driver.  Verified on scipy 1.15 ... 1.18 (the C port of L-BFGS-B with this `setulb` signature, `VERIFIED_SCIPY`); other
+versions are not refused — the self-check decides — but `fit_info['driver']` tells which driver ran.
 """
 import numpy as np
 
@@ -21,6 +22,7 @@ _TASK_FG, _TASK_NEW_X = 3, 1
 
 _FACTR = _FTOL / np.finfo(float).eps
 _checked = None
+VERIFIED_SCIPY = ((1, 15), (1, 18))  # inclusive (major, minor) range the reverse-communication driver was verified on
 _setulb_fn = None
 
 

@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE ONLY — imports the reference's own GP / acquisition modules from
 /root/reference (read-only mount; exists only in the authoring container, never on the GPU box).
 
-Used by `oracle/make_golden.py` to generate the committed fixtures under `tests/golden/` and by
-`tests/test_oracle_vs_reference.py` (skipped when /root/reference is absent).  Nothing in the
+Used by the `oracle/make_golden*.py` scripts to generate the committed fixtures under `tests/golden/` (replayed by
+`tests/test_oracle_golden.py` and the GPU tests).  Nothing in the
 product package may import this module.
 
 Why a shim: `autooed/mobo/__init__.py:1` imports `mobo.py` -> `factory.py` -> `solver/nsga2.py:6`,
