@@ -74,7 +74,7 @@ struct Workspace {
 }  // namespace
 
 struct aoed_gp {
-    int device = 0, d = 0, m = 0, nu = 1, DP = 8;
+    int device = 0, d = 0, m = 0, nu = 1, DP = 8, DE = 8;
     int N = 0, Npad = 0, Kpad = 0, mTiles = 0, JS = 1, jchunk = 0;  // JS: CAPACITY of the training-index split (partials)
     int cap_Npad = 0;  // row capacity the device buffers were allocated for (re-used while N stays in the same 128-bucket)
     int occ_xcov = 2, occ_gradsum = 5;  // resident CTAs per SM of the two thread-per-candidate kernels
@@ -234,32 +234,39 @@ void choose_split(int N, int colTiles, int m, int js_cap, int ctas_per_wave, int
     jchunk = round_up((N + JS - 1) / JS, XC_JT);
 }
 
-template <int NU, int DP>
+// effective width of the thread-per-candidate kernels: DP - 4 when the design fits (see xcov_kernel)
+int pick_de(int d, int DP) { return (DP <= 32 && d <= DP - 4) ? DP - 4 : DP; }
+
+template <int NU, int DP, int DE>
 void launch_xcov(const XcovArgs& a, dim3 grid, bool grad, cudaStream_t s) {
     if (grad)
-        xcov_kernel<NU, DP, true><<<grid, XC_THREADS, 0, s>>>(a);
+        xcov_kernel<NU, DP, true, DE><<<grid, XC_THREADS, 0, s>>>(a);
     else
-        xcov_kernel<NU, DP, false><<<grid, XC_THREADS, 0, s>>>(a);
+        xcov_kernel<NU, DP, false, DE><<<grid, XC_THREADS, 0, s>>>(a);
 }
 
-template <int DP>
+template <int DP, int DE>
 void launch_xcov_nu(int nu, const XcovArgs& a, dim3 grid, bool grad, cudaStream_t s) {
     switch (nu) {
-        case 1: launch_xcov<1, DP>(a, grid, grad, s); break;
-        case 3: launch_xcov<3, DP>(a, grid, grad, s); break;
-        case 5: launch_xcov<5, DP>(a, grid, grad, s); break;
-        default: launch_xcov<-1, DP>(a, grid, grad, s); break;
+        case 1: launch_xcov<1, DP, DE>(a, grid, grad, s); break;
+        case 3: launch_xcov<3, DP, DE>(a, grid, grad, s); break;
+        case 5: launch_xcov<5, DP, DE>(a, grid, grad, s); break;
+        default: launch_xcov<-1, DP, DE>(a, grid, grad, s); break;
     }
 }
 
-void launch_xcov_any(int nu, int DP, const XcovArgs& a, dim3 grid, bool grad, cudaStream_t s) {
-    switch (DP) {
-        case 8: launch_xcov_nu<8>(nu, a, grid, grad, s); break;
-        case 16: launch_xcov_nu<16>(nu, a, grid, grad, s); break;
-        case 24: launch_xcov_nu<24>(nu, a, grid, grad, s); break;
-        case 32: launch_xcov_nu<32>(nu, a, grid, grad, s); break;
-        case 48: launch_xcov_nu<48>(nu, a, grid, grad, s); break;
-        default: launch_xcov_nu<64>(nu, a, grid, grad, s); break;
+void launch_xcov_any(int nu, int DP, int DE, const XcovArgs& a, dim3 grid, bool grad, cudaStream_t s) {
+    switch (DP * 100 + DE) {
+        case 804: launch_xcov_nu<8, 4>(nu, a, grid, grad, s); break;
+        case 808: launch_xcov_nu<8, 8>(nu, a, grid, grad, s); break;
+        case 1612: launch_xcov_nu<16, 12>(nu, a, grid, grad, s); break;
+        case 1616: launch_xcov_nu<16, 16>(nu, a, grid, grad, s); break;
+        case 2420: launch_xcov_nu<24, 20>(nu, a, grid, grad, s); break;
+        case 2424: launch_xcov_nu<24, 24>(nu, a, grid, grad, s); break;
+        case 3228: launch_xcov_nu<32, 28>(nu, a, grid, grad, s); break;
+        case 3232: launch_xcov_nu<32, 32>(nu, a, grid, grad, s); break;
+        case 4848: launch_xcov_nu<48, 48>(nu, a, grid, grad, s); break;
+        default: launch_xcov_nu<64, 64>(nu, a, grid, grad, s); break;
     }
 }
 
@@ -270,35 +277,44 @@ int occ_of(K kernel, int threads) {
     return n;
 }
 
-template <int DP>
-int occ_xcov_nu(int nu) {
+template <int DP, int DE>
+void occ_pair(int nu, int& occ_xcov, int& occ_gradsum) {
     switch (nu) {
-        case 1: return occ_of(xcov_kernel<1, DP, true>, XC_THREADS);
-        case 3: return occ_of(xcov_kernel<3, DP, true>, XC_THREADS);
-        case 5: return occ_of(xcov_kernel<5, DP, true>, XC_THREADS);
-        default: return occ_of(xcov_kernel<-1, DP, true>, XC_THREADS);
+        case 1: occ_xcov = occ_of(xcov_kernel<1, DP, true, DE>, XC_THREADS); break;
+        case 3: occ_xcov = occ_of(xcov_kernel<3, DP, true, DE>, XC_THREADS); break;
+        case 5: occ_xcov = occ_of(xcov_kernel<5, DP, true, DE>, XC_THREADS); break;
+        default: occ_xcov = occ_of(xcov_kernel<-1, DP, true, DE>, XC_THREADS); break;
+    }
+    occ_gradsum = occ_of(gradsum_kernel<DP, DE>, XC_THREADS);
+}
+
+void query_occupancy(int nu, int DP, int DE, int& occ_xcov, int& occ_gradsum) {
+    switch (DP * 100 + DE) {
+        case 804: occ_pair<8, 4>(nu, occ_xcov, occ_gradsum); break;
+        case 808: occ_pair<8, 8>(nu, occ_xcov, occ_gradsum); break;
+        case 1612: occ_pair<16, 12>(nu, occ_xcov, occ_gradsum); break;
+        case 1616: occ_pair<16, 16>(nu, occ_xcov, occ_gradsum); break;
+        case 2420: occ_pair<24, 20>(nu, occ_xcov, occ_gradsum); break;
+        case 2424: occ_pair<24, 24>(nu, occ_xcov, occ_gradsum); break;
+        case 3228: occ_pair<32, 28>(nu, occ_xcov, occ_gradsum); break;
+        case 3232: occ_pair<32, 32>(nu, occ_xcov, occ_gradsum); break;
+        case 4848: occ_pair<48, 48>(nu, occ_xcov, occ_gradsum); break;
+        default: occ_pair<64, 64>(nu, occ_xcov, occ_gradsum); break;
     }
 }
 
-void query_occupancy(int nu, int DP, int& occ_xcov, int& occ_gradsum) {
-    switch (DP) {
-        case 8: occ_xcov = occ_xcov_nu<8>(nu); occ_gradsum = occ_of(gradsum_kernel<8>, XC_THREADS); break;
-        case 16: occ_xcov = occ_xcov_nu<16>(nu); occ_gradsum = occ_of(gradsum_kernel<16>, XC_THREADS); break;
-        case 24: occ_xcov = occ_xcov_nu<24>(nu); occ_gradsum = occ_of(gradsum_kernel<24>, XC_THREADS); break;
-        case 32: occ_xcov = occ_xcov_nu<32>(nu); occ_gradsum = occ_of(gradsum_kernel<32>, XC_THREADS); break;
-        case 48: occ_xcov = occ_xcov_nu<48>(nu); occ_gradsum = occ_of(gradsum_kernel<48>, XC_THREADS); break;
-        default: occ_xcov = occ_xcov_nu<64>(nu); occ_gradsum = occ_of(gradsum_kernel<64>, XC_THREADS); break;
-    }
-}
-
-void launch_gradsum(int DP, const GradsumArgs& a, dim3 grid, cudaStream_t s) {
-    switch (DP) {
-        case 8: gradsum_kernel<8><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 16: gradsum_kernel<16><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 24: gradsum_kernel<24><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 32: gradsum_kernel<32><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 48: gradsum_kernel<48><<<grid, XC_THREADS, 0, s>>>(a); break;
-        default: gradsum_kernel<64><<<grid, XC_THREADS, 0, s>>>(a); break;
+void launch_gradsum(int DP, int DE, const GradsumArgs& a, dim3 grid, cudaStream_t s) {
+    switch (DP * 100 + DE) {
+        case 804: gradsum_kernel<8, 4><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 808: gradsum_kernel<8, 8><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 1612: gradsum_kernel<16, 12><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 1616: gradsum_kernel<16, 16><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 2420: gradsum_kernel<24, 20><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 2424: gradsum_kernel<24, 24><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 3228: gradsum_kernel<32, 28><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 3232: gradsum_kernel<32, 32><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 4848: gradsum_kernel<48, 48><<<grid, XC_THREADS, 0, s>>>(a); break;
+        default: gradsum_kernel<64, 64><<<grid, XC_THREADS, 0, s>>>(a); break;
     }
 }
 
@@ -573,7 +589,7 @@ int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool 
     int JS1, jchunk1, JS2 = 1, jchunk2 = gp->jchunk;
     choose_split(gp->N, colTiles, m, gp->JS, sms * gp->occ_xcov, JS1, jchunk1);
     xa.N = gp->N; xa.Npad = Npad; xa.ldc = ldc; xa.JS = JS1; xa.jchunk = jchunk1;
-    launch_xcov_any(gp->nu, DP, xa, dim3(colTiles, JS1, m), want_grad, s);
+    launch_xcov_any(gp->nu, DP, gp->DE, xa, dim3(colTiles, JS1, m), want_grad, s);
     gp->n_launches++;
     CU(cudaGetLastError());
     if (want_std) {
@@ -592,7 +608,7 @@ int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool 
             ga.V = w.V; ga.Gr = w.Gr; ga.Ts = gp->dTs; ga.part2 = w.part2; ga.strideSlab = slab;
             choose_split(gp->N, colTiles, m, gp->JS, sms * gp->occ_gradsum, JS2, jchunk2);
             ga.N = gp->N; ga.Npad = Npad; ga.ldc = ldc; ga.JS = JS2; ga.jchunk = jchunk2;
-            launch_gradsum(DP, ga, dim3(colTiles, JS2, m), s);
+            launch_gradsum(DP, gp->DE, ga, dim3(colTiles, JS2, m), s);
             gp->n_launches++;
             CU(cudaGetLastError());
         }
@@ -783,7 +799,8 @@ int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu) {
         }
     } guard{gp};
     gp->device = device; gp->d = n_var; gp->m = n_obj; gp->nu = nu; gp->DP = DP;
-    query_occupancy(nu, DP, gp->occ_xcov, gp->occ_gradsum);
+    gp->DE = pick_de(n_var, DP);
+    query_occupancy(nu, DP, gp->DE, gp->occ_xcov, gp->occ_gradsum);
     gp->trmm_variant = trmm_variant_from_env();
     gp->ssf = gp->trmm_variant == 0 ? PT_SS_PER_TILE : 1;
     CU(cudaStreamCreateWithFlags(&gp->streams[0], cudaStreamNonBlocking));

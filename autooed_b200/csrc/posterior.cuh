@@ -48,7 +48,10 @@ struct XcovArgs {
 #define AOED_XCOV_XS_SMEM 0
 #endif
 
-template <int NU, int DP, bool GRAD>
+// DE <= DP: the dimensions the loops run over.  DP fixes the row stride of Ts / the partial-sum layout (8, 16, 24, 32, ...);
+// with n_var <= DP - 4 the instance DE = DP - 4 skips the zero padding (n_var = 20: 17 % of the distance and moment FMAs and
+// 8 registers per thread at DP = 24).
+template <int NU, int DP, bool GRAD, int DE = DP>
 __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(XcovArgs p) {
     __shared__ __align__(16) double ts[XC_JT][DP];
     __shared__ double al[XC_JT];
@@ -61,22 +64,22 @@ __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(X
 
 #if AOED_XCOV_XS_SMEM
     // candidate coordinates in shared memory ([k][thread]: conflict free) instead of 2*DP registers: more resident warps
-    __shared__ double xsm[DP][XC_THREADS];
+    __shared__ double xsm[DE][XC_THREADS];
 #pragma unroll
-    for (int k = 0; k < DP; ++k) xsm[k][tid] = p.XT[int64_t(k) * p.ldc + c] / p.ell[o * DP + k];
+    for (int k = 0; k < DE; ++k) xsm[k][tid] = p.XT[int64_t(k) * p.ldc + c] / p.ell[o * DP + k];
 #define xs(k) xsm[k][tid]
 #else
-    double xsr[DP];
+    double xsr[DE];
 #pragma unroll
-    for (int k = 0; k < DP; ++k) xsr[k] = p.XT[int64_t(k) * p.ldc + c] / p.ell[o * DP + k];
+    for (int k = 0; k < DE; ++k) xsr[k] = p.XT[int64_t(k) * p.ldc + c] / p.ell[o * DP + k];
 #define xs(k) xsr[k]
 #endif
 
     double mu = 0.0, s0 = 0.0;
-    double sk[GRAD ? DP : 1];
+    double sk[GRAD ? DE : 1];
     if (GRAD) {
 #pragma unroll
-        for (int k = 0; k < DP; ++k) sk[k] = 0.0;
+        for (int k = 0; k < DE; ++k) sk[k] = 0.0;
     }
     double* __restrict__ KsT = p.KsT ? p.KsT + o * p.strideSlab : nullptr;
     double* __restrict__ Gr = p.Gr ? p.Gr + o * p.strideSlab : nullptr;
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(X
         for (int jj = 0; jj < nj; ++jj) {
             double r2 = 0.0, r2b = 0.0;
 #pragma unroll
-            for (int k = 0; k < DP; k += 2) {
+            for (int k = 0; k < DE; k += 2) {
                 const double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
                 const double d0 = xs(k) - t.x, d1 = xs(k + 1) - t.y;
                 r2 = fma(d0, d0, r2);
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(X
                 const double wa = w * a;
                 s0 += wa;
 #pragma unroll
-                for (int k = 0; k < DP; k += 2) {
+                for (int k = 0; k < DE; k += 2) {
                     const double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
                     sk[k] = fma(wa, t.x, sk[k]);
                     sk[k + 1] = fma(wa, t.y, sk[k + 1]);
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(X
             const int j1 = two ? jj + 1 : jj;
             double ra0 = 0.0, ra1 = 0.0, rb0 = 0.0, rb1 = 0.0;
 #pragma unroll
-            for (int k = 0; k < DP; k += 2) {
+            for (int k = 0; k < DE; k += 2) {
                 const double2 ta = *reinterpret_cast<const double2*>(&ts[jj][k]);
                 const double2 tb = *reinterpret_cast<const double2*>(&ts[j1][k]);
                 const double a0 = xs(k) - ta.x, a1 = xs(k + 1) - ta.y;
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(X
                 s0 += waa;
                 s0 += wab;
 #pragma unroll
-                for (int k = 0; k < DP; k += 2) {
+                for (int k = 0; k < DE; k += 2) {
                     const double2 ta = *reinterpret_cast<const double2*>(&ts[jj][k]);
                     const double2 tb = *reinterpret_cast<const double2*>(&ts[j1][k]);
                     sk[k] = fma(waa, ta.x, sk[k]);
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(XC_THREADS, AOED_XCOV_MINBLOCKS) xcov_kernel(X
     if (GRAD) {
         part[p.ldc] = s0;
 #pragma unroll
-        for (int k = 0; k < DP; ++k) part[int64_t(2 + k) * p.ldc] = sk[k];
+        for (int k = 0; k < DE; ++k) part[int64_t(2 + k) * p.ldc] = sk[k];
     }
 }
 
@@ -193,7 +196,7 @@ struct GradsumArgs {
     int N, Npad, ldc, JS, jchunk;
 };
 
-template <int DP>
+template <int DP, int DE = DP>
 __global__ void __launch_bounds__(XC_THREADS) gradsum_kernel(GradsumArgs p) {
     __shared__ __align__(16) double ts[XC_JT][DP];
     const int tid = threadIdx.x;
@@ -202,9 +205,9 @@ __global__ void __launch_bounds__(XC_THREADS) gradsum_kernel(GradsumArgs p) {
     const double* __restrict__ Ts = p.Ts + int64_t(o) * p.Npad * DP;
     const double* __restrict__ V = p.V + o * p.strideSlab + c;
     const double* __restrict__ Gr = p.Gr + o * p.strideSlab + c;
-    double s0 = 0.0, sk[DP];
+    double s0 = 0.0, sk[DE];
 #pragma unroll
-    for (int k = 0; k < DP; ++k) sk[k] = 0.0;
+    for (int k = 0; k < DE; ++k) sk[k] = 0.0;
     const int j_begin = js * p.jchunk;
     const int j_end = min(p.N, j_begin + p.jchunk);
     for (int j0 = j_begin; j0 < j_end; j0 += XC_JT) {
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(XC_THREADS) gradsum_kernel(GradsumArgs p) {
                 const int jj = min(jb + u, nj - 1);
                 s0 += wv[u];
 #pragma unroll
-                for (int k = 0; k < DP; k += 2) {
+                for (int k = 0; k < DE; k += 2) {
                     double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
                     sk[k] = fma(wv[u], t.x, sk[k]);
                     sk[k + 1] = fma(wv[u], t.y, sk[k + 1]);
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(XC_THREADS) gradsum_kernel(GradsumArgs p) {
     double* __restrict__ part = p.part2 + (int64_t(o) * p.JS + js) * (1 + DP) * p.ldc + c;
     part[0] = s0;
 #pragma unroll
-    for (int k = 0; k < DP; ++k) part[int64_t(1 + k) * p.ldc] = sk[k];
+    for (int k = 0; k < DE; ++k) part[int64_t(1 + k) * p.ldc] = sk[k];
 }
 
 // Transposes the candidate chunk [rows][d] (row-major, as numpy hands it over) to [DP][ldc].
