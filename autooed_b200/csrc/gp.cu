@@ -191,7 +191,9 @@ int ensure_ws(aoed_gp* gp, Workspace& w, int64_t cols, bool staging) {
         CU(cudaMemset(w.V, 0, slab));
         CU(cudaMalloc(&w.sumsq, size_t(m) * gp->mTiles * gp->ssf * cols * sizeof(double)));
         CU(cudaMalloc(&w.part, size_t(m) * gp->JS * (2 + DP) * cols * sizeof(double)));
-        CU(cudaMalloc(&w.part2, size_t(m) * gp->JS * (1 + DP) * cols * sizeof(double)));
+        // gradient moments of the variance: one slice per training-index split (gradsum_kernel) or per 32-row warp slice of the
+        // UPPER product when they are fused into its epilogue
+        CU(cudaMalloc(&w.part2, size_t(m) * std::max(gp->JS, gp->mTiles * gp->ssf) * (1 + DP) * cols * sizeof(double)));
         if (gp->trmm_variant == 0) {
             CHK(make_map_2d(&w.mapKsT, w.KsT, int64_t(m) * Npad, cols, cols, TK));
             CHK(make_map_2d(&w.mapW, w.W, int64_t(m) * Npad, cols, cols, TK));
@@ -436,9 +438,17 @@ int sm_count(int device) {
 
 // `ticket`: the launch's tile counter; it must not be shared with a launch that can still be running on ANOTHER stream
 // (launches on one stream are ordered, so a per-stream counter or ring is safe).
+// optional fused epilogue of the UPPER product (variance-gradient moments, see TrmmTmaArgs)
+struct FusedMoments {
+    const double* Gr = nullptr;
+    const double* Ts = nullptr;
+    double* part2 = nullptr;
+    int DPs = 0, dims = 0;
+};
+
 template <bool UPPER>
 int launch_trmm_tma(aoed_gp* gp, const CUtensorMap& mapA, const CUtensorMap& mapB, const TrmmArgs& a, int colTiles,
-                    int batch, cudaStream_t s, int* ticket = nullptr) {
+                    int batch, cudaStream_t s, int* ticket = nullptr, const FusedMoments* fm = nullptr) {
     static bool attr_set[64] = {false};  // function attributes are per device
     const int dev = gp->device & 63;
     if (!attr_set[dev]) {
@@ -449,6 +459,8 @@ int launch_trmm_tma(aoed_gp* gp, const CUtensorMap& mapA, const CUtensorMap& map
     t.Out = a.Out; t.strideOut = a.strideOut; t.ldo = a.ldo;
     t.sumsq = a.sumsq; t.strideSS = a.strideSS;
     t.M = a.M; t.Kpad = a.Kpad; t.Npad = gp->Npad; t.mTiles = a.mTiles; t.colTiles = colTiles; t.batch = batch;
+    t.Gr = fm ? fm->Gr : nullptr; t.Ts = fm ? fm->Ts : nullptr; t.part2 = fm ? fm->part2 : nullptr;
+    t.DPs = fm ? fm->DPs : 0; t.dims = fm ? fm->dims : 0;
     if (ticket == nullptr) {  // evaluation path: ring on the (single) compute stream
         gp->ticket_slot = (gp->ticket_slot + 1) % 64;
         ticket = gp->dTickets + gp->ticket_slot;
@@ -485,10 +497,10 @@ int launch_trmm_tma(aoed_gp* gp, const CUtensorMap& mapA, const CUtensorMap& map
 
 // `colTiles` counts 128-column groups of the slab; mapB must view the slab passed as a.B
 int launch_trmm(aoed_gp* gp, bool upper, const TrmmArgs& a, const CUtensorMap& mapB, int colTiles, int batch,
-                cudaStream_t s) {
+                cudaStream_t s, const FusedMoments* fm = nullptr) {
     if (gp->profiling) CU(cudaEventRecord(gp->ev0, s));
     if (gp->trmm_variant == 0) {
-        if (upper) CHK(launch_trmm_tma<true>(gp, gp->mapLinvT, mapB, a, colTiles, batch, s));
+        if (upper) CHK(launch_trmm_tma<true>(gp, gp->mapLinvT, mapB, a, colTiles, batch, s, nullptr, fm));
         else CHK(launch_trmm_tma<false>(gp, gp->mapLinv, mapB, a, colTiles, batch, s));
     } else if (gp->trmm_variant == 128) {
         if (upper) CHK((launch_trmm_cfg<true, 128>(a, colTiles, batch, s)));
@@ -569,7 +581,7 @@ int eval_small(aoed_gp* gp, const double* d_X, int64_t rows, bool want_std, cons
 
 // One chunk of `rows` candidates (rows <= ws.cols), device-resident, row-major input d_X[rows][d].
 int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool want_std, bool want_grad,
-               const AcqDev& acq, const EvalOut& out, cudaStream_t s) {
+               const AcqDev& acq, const EvalOut& out, cudaStream_t s, bool keep_V = false) {
     if (small_eval_applies(gp, rows, want_grad)) return eval_small(gp, d_X, rows, want_std, acq, out, s);
     const int m = gp->m, DP = gp->DP, Npad = gp->Npad;
     const int ldc = int(w.cols);
@@ -603,14 +615,29 @@ int eval_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, bool 
         if (want_grad) {
             TrmmArgs u = t;
             u.A = gp->dLinvT; u.B = w.W; u.Out = w.V; u.sumsq = nullptr;
-            CHK(launch_trmm(gp, true, u, w.mapW, colTiles, m, s));
-            GradsumArgs ga;
-            ga.V = w.V; ga.Gr = w.Gr; ga.Ts = gp->dTs; ga.part2 = w.part2; ga.strideSlab = slab;
-            choose_split(gp->N, colTiles, m, gp->JS, sms * gp->occ_gradsum, JS2, jchunk2);
-            ga.N = gp->N; ga.Npad = Npad; ga.ldc = ldc; ga.JS = JS2; ga.jchunk = jchunk2;
-            launch_gradsum(DP, gp->DE, ga, dim3(colTiles, JS2, m), s);
-            gp->n_launches++;
-            CU(cudaGetLastError());
+            // AOED_GRADSUM=fused forms the moments sum_j Gr_j v_j [ts_jk] from the accumulators in the epilogue of the persistent
+            // UPPER product (v never leaves the SM, no gradsum launch, 1.4 GB less HBM traffic per 16384-candidate chunk).
+            // Parity-tested, but NOT the default: measured at c4 it costs +11 % on the UPPER launches (6.15 instead of 5.83 ms
+            // average launch, step 852 instead of 834 ms) — all 16 consumer warps reach their epilogues together and the
+            // 21 dependent load -> FMA -> shuffle rounds of the slowest warp stall the whole TMA ring, which is worth more
+            // than the 28 ms the separate HBM-bound kernel takes (profiles/bench_fused_gradsum_r02.json).
+            static const bool fused = getenv("AOED_GRADSUM") && strcmp(getenv("AOED_GRADSUM"), "fused") == 0;
+            if (gp->trmm_variant == 0 && fused) {
+                FusedMoments fm;
+                fm.Gr = w.Gr; fm.Ts = gp->dTs; fm.part2 = w.part2; fm.DPs = DP; fm.dims = gp->d;
+                if (!keep_V) u.Out = nullptr;
+                CHK(launch_trmm(gp, true, u, w.mapW, colTiles, m, s, &fm));
+                JS2 = gp->mTiles * gp->ssf;
+            } else {
+                CHK(launch_trmm(gp, true, u, w.mapW, colTiles, m, s));
+                GradsumArgs ga;
+                ga.V = w.V; ga.Gr = w.Gr; ga.Ts = gp->dTs; ga.part2 = w.part2; ga.strideSlab = slab;
+                choose_split(gp->N, colTiles, m, gp->JS, sms * gp->occ_gradsum, JS2, jchunk2);
+                ga.N = gp->N; ga.Npad = Npad; ga.ldc = ldc; ga.JS = JS2; ga.jchunk = jchunk2;
+                launch_gradsum(DP, gp->DE, ga, dim3(colTiles, JS2, m), s);
+                gp->n_launches++;
+                CU(cudaGetLastError());
+            }
         }
     }
     EpilogueArgs e;
@@ -712,7 +739,7 @@ int eval_hess_chunk(aoed_gp* gp, Workspace& w, const double* d_X, int64_t rows, 
         if (!in.S) in.S = w.bS;
         if (!in.dS) in.dS = w.bdS;
     }
-    CHK(eval_chunk(gp, w, d_X, rows, want_std, true, acq, in, s));
+    CHK(eval_chunk(gp, w, d_X, rows, want_std, true, acq, in, s, /*keep_V=*/true));
     const bool exact = acq.exact != 0;
     if (want_std) {
         DkcolArgs da;

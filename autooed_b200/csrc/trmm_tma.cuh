@@ -87,6 +87,12 @@ struct TrmmTmaArgs {
     int* counter;     // tile ticket counter, zeroed before the launch
     int* dbg;         // host-mapped diagnostics (who timed out where), or nullptr
     int colGroup;     // column tiles whose B panels (all batches) are meant to stay L2-resident together
+    // fused gradient moments of the variance (UPPER product only; replaces gradsum_kernel, gp.py:201-205): with
+    // p = Gr[row][col] * Out[row][col], per 32-row warp slice and column  sum_rows p  and  sum_rows p * Ts[row][k], k < dims
+    const double* Gr;   // [batch][rows][ldo] (same strides as Out) or nullptr
+    const double* Ts;   // [batch][Npad][DPs] training points divided by the length scales
+    double* part2;      // [batch][mTiles * 4][1 + DPs][ldo]
+    int DPs, dims;
 };
 
 constexpr int PT_COL_GROUP = 8;  // default colGroup (AOED_TRMM_COLGROUP overrides)
@@ -255,6 +261,77 @@ trmm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         *reinterpret_cast<double2*>(dst) = make_double2(acc[mb][2 * pp][0], acc[mb][2 * pp + 1][0]);
                         *reinterpret_cast<double2*>(dst + 2) = make_double2(acc[mb][2 * pp][1], acc[mb][2 * pp + 1][1]);
                     }
+                }
+            }
+        }
+        if (UPPER && p.part2 != nullptr) {
+            // ---- fused variance-gradient moments: the warp's 32 x 32 sub-tile of V never has to be re-read from HBM ----
+            const double* __restrict__ Gr = p.Gr + b * p.strideOut;
+            const double* __restrict__ Ts = p.Ts + int64_t(b) * p.Npad * p.DPs;
+            const int row0 = mt * TM + wm * 32 + rho;
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) {  // acc <- Gr * V (rows in the zero padding contribute nothing)
+                const int row = row0 + mb * 8;
+                const bool live = row < p.M;
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    double2 g0 = make_double2(0.0, 0.0), g1 = g0;
+                    if (live) {
+                        const double* src = Gr + int64_t(row) * p.ldo + ct * 128 + wn * 32 + 16 * pp + 4 * q;
+                        g0 = *reinterpret_cast<const double2*>(src);
+                        g1 = *reinterpret_cast<const double2*>(src + 2);
+                    }
+                    acc[mb][2 * pp][0] *= g0.x;
+                    acc[mb][2 * pp + 1][0] *= g0.y;
+                    acc[mb][2 * pp][1] *= g1.x;
+                    acc[mb][2 * pp + 1][1] *= g1.y;
+                }
+            }
+            double* __restrict__ P2 = p.part2 + (int64_t(b) * p.mTiles * PT_SS_PER_TILE + mt * PT_SS_PER_TILE + wm) * int64_t(1 + p.DPs) * p.ldo +
+                                      ct * 128 + wn * 32 + 16 * (g >> 2) + 4 * q + (g & 3);
+            // three moments per pass: their twelve Ts loads (L2 hits, ~500 cycles) are in flight together
+            for (int kk0 = 0; kk0 <= p.dims; kk0 += 3) {
+                double t[3][4];
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+#pragma unroll
+                    for (int mb = 0; mb < 4; ++mb) {
+                        const int row = row0 + mb * 8, kk = kk0 + u;
+                        t[u][mb] = (kk == 0) ? 1.0 : ((row < p.M && kk <= p.dims) ? Ts[int64_t(row) * p.DPs + kk - 1] : 0.0);
+                    }
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int kk = kk0 + u;
+                    // s8[j]: column j = 4 pp + 2 e + (nb & 1) of the lane's eight, summed over its four rows
+                    double s8[8];
+#pragma unroll
+                    for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const int nb = 2 * pp + (j4 & 1), e = j4 >> 1;
+                            double v = acc[0][nb][e] * t[u][0];
+#pragma unroll
+                            for (int mb = 1; mb < 4; ++mb) v = fma(acc[mb][nb][e], t[u][mb], v);
+                            s8[4 * pp + j4] = v;
+                        }
+                    // reduce over the eight lane groups (rows) and scatter: lane group g ends up with column j = g
+                    double s4[4], s2[2];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double give = (g & 4) ? s8[j] : s8[j + 4];
+                        const double keep = (g & 4) ? s8[j + 4] : s8[j];
+                        s4[j] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const double give = (g & 2) ? s4[j] : s4[j + 2];
+                        const double keep = (g & 2) ? s4[j + 2] : s4[j];
+                        s2[j] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+                    }
+                    const double give = (g & 1) ? s2[0] : s2[1];
+                    const double keep = (g & 1) ? s2[1] : s2[0];
+                    const double tot = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+                    if (kk <= p.dims) P2[int64_t(kk) * p.ldo] = tot;
                 }
             }
         }
