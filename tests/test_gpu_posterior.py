@@ -407,3 +407,39 @@ def test_small_batch_kernel_equals_chunked_path(nu, N, d, rows, monkeypatch):
     ok = v0.min(axis=1) > 1e-6 * prior  # acquisitions divide by sigma: compare where sigma is not cancellation noise
     for k in range(3, 7):
         assert np.allclose(res["1"][k][ok], res["0"][k][ok], rtol=1e-8, atol=1e-10 * scale + 10 * mean_tol)
+
+
+def test_fused_gradient_moments_equal_separate_kernel(tmp_path):
+    """AOED_GRADSUM=fused (variance-gradient moments formed in the epilogue of the UPPER triangular product) against the
+    default gradsum kernel: same dS / dA up to summation order.  The switch is latched per process: child process."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = f"""
+import sys, numpy as np
+sys.path[:0] = [{here!r}, {os.path.dirname(here)!r}]
+from autooed_b200 import GaussianProcess, UpperConfidenceBound
+from autooed_b200.problem import SimpleProblem
+rng = np.random.default_rng(0)
+N, d, m = 300, 7, 2
+X = rng.random((N, d)); Y = np.sin(X @ rng.standard_normal((d, m))) + 0.05 * rng.standard_normal((N, m))
+th = np.tile(np.concatenate([[0.0], np.full(d, -0.3), [-4.0]]), (m, 1))
+gp = GaussianProcess(SimpleProblem(d, m), nu=5); gp.fit_fixed(X, Y, th)
+acq = UpperConfidenceBound(gp); acq.fit(X, Y)
+Xs = rng.random((700, d))
+out = gp.evaluate(Xs, std=True, gradient=True)
+A, dA, _ = acq.evaluate(Xs, gradient=True)
+np.savez(sys.argv[1], S=out['S'], dS=out['dS'], dF=out['dF'], A=A, dA=dA)
+"""
+    res = {}
+    for mode in ("separate", "fused"):
+        path = str(tmp_path / f"{mode}.npz")
+        env = dict(os.environ, AOED_GRADSUM=mode)
+        r = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[mode] = dict(np.load(path))
+    for k in ("S", "dF", "A"):
+        assert np.array_equal(res["fused"][k], res["separate"][k]), k
+    for k in ("dS", "dA"):
+        assert np.allclose(res["fused"][k], res["separate"][k], rtol=1e-9, atol=1e-12), k
+    assert np.abs(res["fused"]["dS"]).max() > 0
