@@ -53,8 +53,9 @@ constexpr int NS_MAX_D = 32;
 
 struct VarArgs {
     const double* X;      // [n_cur][d] current population (continuous)
-    const int* rank;      // [n_cur]
+    const double* F;      // [n_cur][m] its acquisition values
     const double* crowd;  // [n_cur]
+    int m;
     const double *xl, *xu;
     double* Xoff;         // [P][d] offspring (continuous)
     int n_cur, P, d;
@@ -63,12 +64,19 @@ struct VarArgs {
     double pc, eta_c, eta_m;
 };
 
+// pymoo 0.4.1 NSGA2: binary tournament of type 'comp_by_dom_and_crowding' — the contestant that DOMINATES the other wins
+// (Dominator.get_relation on the objective vectors), otherwise the larger crowding distance, a coin on ties
 __device__ __forceinline__ int tournament(curandStatePhilox4_32_10_t& st, const VarArgs& p) {
     const int a = min(int(curand_uniform_double(&st) * p.n_cur), p.n_cur - 1);
     const int b = min(int(curand_uniform_double(&st) * p.n_cur), p.n_cur - 1);
     const double coin = curand_uniform_double(&st);
-    const int ra = p.rank[a], rb = p.rank[b];
-    if (ra != rb) return ra < rb ? a : b;
+    bool a_lt = false, b_lt = false;
+    for (int t = 0; t < p.m; ++t) {
+        const double fa = p.F[int64_t(a) * p.m + t], fb = p.F[int64_t(b) * p.m + t];
+        a_lt = a_lt || fa < fb;
+        b_lt = b_lt || fb < fa;
+    }
+    if (a_lt != b_lt) return a_lt ? a : b;
     const double ca = p.crowd[a], cb = p.crowd[b];
     if (ca != cb) return ca > cb ? a : b;
     return coin < 0.5 ? a : b;
@@ -502,7 +510,7 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
     NCU(cudaMemcpyAsync(bGen.p, &one, sizeof(int), cudaMemcpyHostToDevice, s));
     auto generation = [&]() -> int {
         VarArgs va;
-        va.X = bX[cur].as<double>(); va.rank = bR[cur].as<int>(); va.crowd = bC[cur].as<double>();
+        va.X = bX[cur].as<double>(); va.F = bF[cur].as<double>(); va.m = m; va.crowd = bC[cur].as<double>();
         va.xl = bXl.as<double>(); va.xu = bXu.as<double>(); va.Xoff = bXoff.as<double>();
         va.n_cur = n_cur; va.P = P; va.d = d; va.seed = seed; va.gen = bGen.as<int>(); va.pc = 0.9; va.eta_c = 15.0; va.eta_m = 20.0;
         mark(0);

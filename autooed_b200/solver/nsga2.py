@@ -3,7 +3,8 @@
 Reference: `autooed/mobo/solver/nsga2.py:13-30` delegates to pymoo 0.4.1 `NSGA2(pop_size)` + `minimize(..., ('n_gen', G))`.
 pymoo is not part of this repository, so the algorithm is written out here with pymoo 0.4.1's defaults (SURVEY.md
 Appendix F): the initial population is the given sampling as is — all of it (ranked) parents the first offspring, the cut to
-pop_size happens at the first merge, as pymoo's `_initialize` runs its survival with n_survive = len(pop); binary tournament on (rank, crowding distance);
+pop_size happens at the first merge, as pymoo's `_initialize` runs its survival with n_survive = len(pop); binary tournament of pymoo's default type
+'comp_by_dom_and_crowding' (the dominating contestant, else the larger crowding distance);
 simulated binary crossover (prob 0.9, eta 15, per-variable exchange prob 0.5); polynomial mutation (eta 20, prob
 1/n_var); duplicate elimination; n_offsprings = pop_size; rank-and-crowding survival; generation 1 is the evaluation of
 the initial population.  Populations are NOT seed-for-seed identical with pymoo (different RNG call order); every
@@ -48,12 +49,15 @@ class NSGA2Algorithm:
         self.n_eval = 0
 
     # -- variation -------------------------------------------------------------------------------------------------
-    def _tournament(self, rank, crowd, n, cv=None):
-        """Binary tournament (pymoo `binary_tournament`): if either contestant violates a constraint the smaller violation
-        wins (random on ties); between feasible ones rank, then crowding distance, random on ties."""
-        a, b = np.random.randint(len(rank), size=n), np.random.randint(len(rank), size=n)
-        better = (rank[a] < rank[b]) | ((rank[a] == rank[b]) & (crowd[a] > crowd[b]))
-        tie = (rank[a] == rank[b]) & (crowd[a] == crowd[b])
+    def _tournament(self, F, crowd, n, cv=None):
+        """Binary tournament (pymoo 0.4.1 `binary_tournament`, type 'comp_by_dom_and_crowding'): if either contestant
+        violates a constraint the smaller violation wins; between feasible ones the one that DOMINATES the other
+        (`Dominator.get_relation` on the objective vectors), else the larger crowding distance; a coin on ties."""
+        a, b = np.random.randint(len(F), size=n), np.random.randint(len(F), size=n)
+        a_lt, b_lt = (F[a] < F[b]).any(axis=1), (F[b] < F[a]).any(axis=1)
+        decided = a_lt != b_lt
+        better = np.where(decided, a_lt, crowd[a] > crowd[b])
+        tie = ~decided & (crowd[a] == crowd[b])
         if cv is not None:
             infeas = (cv[a] > 0.0) | (cv[b] > 0.0)
             better = np.where(infeas, cv[a] < cv[b], better)
@@ -174,8 +178,8 @@ class NSGA2Algorithm:
                 if need <= 0:
                     break
                 n_pairs = (need + 1) // 2
-                pa = self._tournament(rank, crowd, n_pairs, cv)
-                pb = self._tournament(rank, crowd, n_pairs, cv)
+                pa = self._tournament(F, crowd, n_pairs, cv)
+                pb = self._tournament(F, crowd, n_pairs, cv)
                 c1, c2 = self._sbx(X[pa], X[pb], xl, xu)
                 cand = self._mutate(np.vstack([c1, c2])[:need], xl, xu)
                 off = np.vstack([off, self._drop_duplicates(cand, np.vstack([X, off]))])

@@ -268,6 +268,8 @@ def run_ours(args):
         guarded("fit_c4", extra_fit_c4, gp_model=(X, Y), **ctxt)
         if world > 1:
             guarded("sharded_eval", extra_sharded_eval, gp, dX, **ctxt)
+        if world > 1:
+            guarded("sharded_selection", extra_sharded_selection, **ctxt)
         guarded("c5", extra_c5, **ctxt)
         if rank == 0:
             guarded("mobo", extra_mobo)
@@ -452,6 +454,44 @@ def extra_sharded_eval(gp, dX_local, torch, dist, world, rank, local, dev, barri
                                 "collective": "2 x ncclAllGather (in place) per call"}}
     del dX, A, dA
     return res
+
+
+def extra_sharded_selection(torch, dist, world, rank, local, dev, barrier, args):
+    """SURVEY.md §8(e) rows 3-4 on real devices: greedy HVI batch selection with the candidates sharded (one
+    (contribution, index) pair per rank and round over NCCL) and the non-dominated mask with the rows sharded; rank 0 repeats
+    both on its own GPU and compares."""
+    from autooed_b200.selection.hvi import hvi_select_indices
+    from autooed_b200.sharding import hvi_select_sharded, pareto_mask_sharded
+    from autooed_b200.utils.pareto import check_pareto
+    rng = np.random.default_rng(7)  # the same data on every rank
+    m, C, N, batch = 3, 1 << 17, 2000, 8
+    Y = rng.random((N, m)) * 0.5 + 0.5
+    Yc = rng.random((C, m)) ** 0.5
+    out = {}
+    for rep in range(2):
+        np.random.seed(11)
+        barrier()
+        t0 = time.perf_counter()
+        idx = hvi_select_sharded(Yc, Y, batch)
+        (t_hvi,) = _max_over_ranks(torch, dist, world, dev, [time.perf_counter() - t0])
+        barrier()
+        t0 = time.perf_counter()
+        mask = pareto_mask_sharded(Yc)
+        (t_par,) = _max_over_ranks(torch, dist, world, dev, [time.perf_counter() - t0])
+    if rank == 0:
+        np.random.seed(11)
+        t0 = time.perf_counter()
+        idx1 = hvi_select_indices(Yc, Y, batch, device=local)
+        t1 = time.perf_counter() - t0
+        mask1 = check_pareto(Yc, device=local)
+        out["sharded_selection"] = {"candidates": C, "n_obj": m, "batch": batch, "world": world,
+                                    "hvi_sharded_ms": 1e3 * t_hvi, "hvi_single_gpu_ms": 1e3 * t1,
+                                    "hvi_batch_equals_single": bool(list(idx) == list(idx1)),
+                                    "pareto_mask_sharded_ms": 1e3 * t_par, "pareto_mask_equals_single": bool(np.array_equal(mask, mask1)),
+                                    "collectives": "all_gather of one (contribution, index) pair per rank and round; all_gather of mask shards",
+                                    "note": "the sharded HVI path scores shards with one host-synchronised call per round; the single-GPU "
+                                            "path keeps all rounds on the device, so it is the faster one at this size"}
+    return out
 
 
 def extra_c5(torch, dist, world, rank, local, dev, barrier, args):

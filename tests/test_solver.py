@@ -80,8 +80,11 @@ def test_nsga2_is_feasibility_first_on_constrained_problems():
     assert list(rank) == [0, 0, 1, 2, 2]
     # tournament: an infeasible contestant never beats a feasible one, whatever its rank
     np.random.seed(3)
-    picks = alg._tournament(np.array([5, 0]), np.array([0.0, 9.0]), 2000, cv=np.array([0.0, 0.4]))
-    assert not (picks == 1).any() or set(np.unique(picks)) <= {0, 1} and (picks == 1).mean() < 0.3
+    picks = alg._tournament(np.array([[5.0, 5.0], [0.0, 0.0]]), np.array([0.0, 9.0]), 2000, cv=np.array([0.0, 0.4]))
+    assert (picks == 1).mean() < 0.3  # index 1 only wins its duels against itself
+    # feasible contestants: the dominating one wins whatever the crowding distances say
+    picks = alg._tournament(np.array([[1.0, 1.0], [0.5, 0.5]]), np.array([9.0, 0.0]), 2000)
+    assert (picks == 0).mean() < 0.3
     # whole loop: the final population is feasible and still spreads along the constrained front
     alg = NSGA2Algorithm(pop_size=40, rank_fn=mo.pareto_rank)
     prob = ConstrainedZdt1()
