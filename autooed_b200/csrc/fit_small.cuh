@@ -26,6 +26,7 @@ constexpr int FS_MAX_N = 232;
 
 struct LmlSmallArgs {
     const double* X;       // [N][d] normalised training inputs
+    const double* XT;      // [d][Npad] the same, dimension-major and zero padded (coalesced 4 x 4 pair blocks in lml_blk_kernel)
     const double* Y;       // [m][Npad] normalised targets, objective-major
     const double* theta;   // [B][d+2]
     const int* obj;        // [B]

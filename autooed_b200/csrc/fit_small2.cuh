@@ -101,19 +101,53 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_blk_kernel(LmlSmallArgs p) 
     auto LP = [&](int i, int j) -> double { return (i < N && j <= i) ? Lp[tri(i) + j] : 0.0; };
 
     // ---- 1: kernel matrix ---------------------------------------------------------------------------------------
-    for (int i = warp; i < N; i += FS_WARPS) {
-        const double* xi = p.X + int64_t(i) * d;
-        for (int j = lane; j <= i; j += 32) {
-            const double* xj = p.X + int64_t(j) * d;
-            double r2 = 0.0;
-            for (int k = 0; k < d; ++k) {
-                const double t = (xi[k] - xj[k]) * iell[k];
-                r2 = fma(t, t, r2);
-            }
-            double phi, gor;
-            kernel_profile<NU>(sqrt(r2), r2, phi, gor);
-            Lp[tri(i) + j] = (i == j) ? (c1 + c2) + kJitter : fma(c1, phi, c2);
+    // 4 x 4 pair blocks on or below the diagonal, one per thread and step: per coordinate two 32-byte loads from the
+    // dimension-major copy of X serve 16 pairs (consecutive threads take consecutive column blocks: coalesced)
+    const int nb4 = (N + 3) >> 2, nblk4 = nb4 * (nb4 + 1) / 2;
+    auto block_of = [&](int t, int& i0, int& j0) {
+        int bi = int((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while (bi * (bi + 1) / 2 > t) --bi;
+        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+        i0 = 4 * bi;
+        j0 = 4 * (t - bi * (bi + 1) / 2);
+    };
+    // squared scaled distances of the block's 16 pairs: direct differences times 1/l, as cdist(X / l, X / l) forms them
+    auto block_r2 = [&](int i0, int j0, double (&r2)[4][4]) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) r2[r][c] = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double* row = p.XT + int64_t(k) * p.Npad;
+            const double2 a01 = *reinterpret_cast<const double2*>(row + i0), a23 = *reinterpret_cast<const double2*>(row + i0 + 2);
+            const double2 b01 = *reinterpret_cast<const double2*>(row + j0), b23 = *reinterpret_cast<const double2*>(row + j0 + 2);
+            const double a[4] = {a01.x, a01.y, a23.x, a23.y}, bq[4] = {b01.x, b01.y, b23.x, b23.y};
+            const double sc = iell[k];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double t = (a[r] - bq[c]) * sc;
+                    r2[r][c] = fma(t, t, r2[r][c]);
+                }
         }
+    };
+    for (int t = tid; t < nblk4; t += FS_THREADS) {
+        int i0, j0;
+        block_of(t, i0, j0);
+        double r2[4][4];
+        block_r2(i0, j0, r2);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = i0 + r, j = j0 + c;
+                if (i < N && j <= i) {
+                    double phi, gor;
+                    kernel_profile<NU>(sqrt(r2[r][c]), r2[r][c], phi, gor);
+                    Lp[tri(i) + j] = (i == j) ? (c1 + c2) + kJitter : fma(c1, phi, c2);
+                }
+            }
     }
     __syncthreads();
     FB_STAMP(1)
@@ -360,33 +394,54 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_blk_kernel(LmlSmallArgs p) 
     }
 
     // ---- 5b: gradient contraction ---------------------------------------------------------------------------------------
+    // the same 4 x 4 pair blocks: distances, then the weights w (alpha alpha^T - K^-1, off-diagonal pairs twice) times the
+    // kernel derivatives, then a second sweep over the coordinates for the length-scale components
     double gacc[DP + 2];
 #pragma unroll
     for (int k = 0; k < DP + 2; ++k) gacc[k] = 0.0;
-    for (int i = warp; i < N; i += FS_WARPS) {
-        const double* xi = p.X + int64_t(i) * d;
-        const double ai = al[i];
-        for (int j = lane; j <= i; j += 32) {
-            double w = ai * al[j] - Lp[tri(i) + j];
-            if (i != j) w *= 2.0;
-            const double* xj = p.X + int64_t(j) * d;
-            double r2 = 0.0;
-            for (int k = 0; k < d; ++k) {
-                const double t = (xi[k] - xj[k]) * iell[k];
-                r2 = fma(t, t, r2);
-            }
-            const double r = sqrt(r2);
-            double phi, gor;
-            kernel_profile<NU>(r, r2, phi, gor);
-            if (i == j) phi = 1.0;
-            gacc[0] = fma(w * c1, phi, gacc[0]);
-            const double wh = w * c1 * h_profile<NU>(r, r2, phi);
+    for (int t = tid; t < nblk4; t += FS_THREADS) {
+        int i0, j0;
+        block_of(t, i0, j0);
+        double wh[4][4];  // squared distance first, then w * c1 * h(r)
+        block_r2(i0, j0, wh);
 #pragma unroll
-            for (int k = 0; k < DP; ++k) {
-                const double t = (k < d) ? (xi[k] - xj[k]) * iell[k] : 0.0;
-                gacc[1 + k] = fma(wh, t * t, gacc[1 + k]);
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = i0 + r, j = j0 + c;
+                double whv = 0.0;
+                if (i < N && j <= i) {
+                    double w = al[i] * al[j] - Lp[tri(i) + j];
+                    if (i != j) w *= 2.0;
+                    const double r2v = wh[r][c], rr = sqrt(r2v);
+                    double phi, gor;
+                    kernel_profile<NU>(rr, r2v, phi, gor);
+                    if (i == j) phi = 1.0;
+                    gacc[0] = fma(w * c1, phi, gacc[0]);
+                    gacc[DP + 1] = fma(w, c2, gacc[DP + 1]);
+                    whv = w * c1 * h_profile<NU>(rr, r2v, phi);
+                }
+                wh[r][c] = whv;
             }
-            gacc[DP + 1] = fma(w, c2, gacc[DP + 1]);
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+            if (k < d) {
+                const double* row = p.XT + int64_t(k) * p.Npad;
+                const double2 a01 = *reinterpret_cast<const double2*>(row + i0), a23 = *reinterpret_cast<const double2*>(row + i0 + 2);
+                const double2 b01 = *reinterpret_cast<const double2*>(row + j0), b23 = *reinterpret_cast<const double2*>(row + j0 + 2);
+                const double a[4] = {a01.x, a01.y, a23.x, a23.y}, bq[4] = {b01.x, b01.y, b23.x, b23.y};
+                const double sc = iell[k];
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; c += 2) {
+                        const double t0 = (a[r] - bq[c]) * sc, t1 = (a[r] - bq[c + 1]) * sc;
+                        s0 = fma(wh[r][c], t0 * t0, s0);
+                        s1 = fma(wh[r][c + 1], t1 * t1, s1);
+                    }
+                gacc[1 + k] += s0 + s1;
+            }
         }
     }
 #pragma unroll

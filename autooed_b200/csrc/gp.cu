@@ -82,6 +82,7 @@ struct aoed_gp {
     std::vector<double> theta, y_mean, y_scale, lml, Xn, Yn;
     // device model state
     double *dX = nullptr, *dY = nullptr;  // [N][d], [m][Npad]
+    double* dXT = nullptr;                // [d][Npad] dimension-major copy of dX, zero padded
     double *dTs = nullptr, *dAlpha = nullptr, *dEll = nullptr, *dLinv = nullptr, *dLinvT = nullptr, *dL = nullptr;
     ModelDev* dModel = nullptr;
     double* dC1C2 = nullptr;        // [m][2]
@@ -141,7 +142,7 @@ void free_blocked(aoed_gp* gp) {
 }
 
 void free_model(aoed_gp* gp) {
-    double** ptrs[] = {&gp->dX, &gp->dY, &gp->dTs, &gp->dAlpha, &gp->dEll, &gp->dLinv, &gp->dLinvT, &gp->dL, &gp->dC1C2};
+    double** ptrs[] = {&gp->dX, &gp->dXT, &gp->dY, &gp->dTs, &gp->dAlpha, &gp->dEll, &gp->dLinv, &gp->dLinvT, &gp->dL, &gp->dC1C2};
     for (auto pp : ptrs) {
         if (*pp) cudaFree(*pp);
         *pp = nullptr;
@@ -895,6 +896,7 @@ int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const doub
     const size_t Np = gp->Npad;
     if (!reuse) {
         CU(cudaMalloc(&gp->dX, Np * d * sizeof(double)));
+        CU(cudaMalloc(&gp->dXT, Np * d * sizeof(double)));
         CU(cudaMalloc(&gp->dY, size_t(m) * Np * sizeof(double)));
         CU(cudaMalloc(&gp->dTs, size_t(m) * Np * gp->DP * sizeof(double)));
         CU(cudaMalloc(&gp->dAlpha, size_t(m) * Np * sizeof(double)));
@@ -924,6 +926,12 @@ int aoed_gp_set_train(aoed_gp_t* gp, int n_train, const double* h_Xn, const doub
         CU(cudaDeviceSynchronize());
     }
     CU(cudaMemcpy(gp->dX, h_Xn, size_t(N) * d * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> xt(Np * d, 0.0);
+        for (int i = 0; i < N; ++i)
+            for (int k = 0; k < d; ++k) xt[size_t(k) * Np + i] = h_Xn[size_t(i) * d + k];
+        CU(cudaMemcpy(gp->dXT, xt.data(), xt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     std::vector<double> yt(size_t(m) * Np, 0.0);
     for (int o = 0; o < m; ++o)
         for (int i = 0; i < N; ++i) yt[size_t(o) * Np + i] = h_Yn[size_t(i) * m + o];
@@ -1132,7 +1140,7 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
     if (small) {
         // one CTA per problem, everything in shared memory
         LmlSmallArgs a;
-        a.X = gp->dX; a.Y = gp->dY; a.theta = gp->dThetaB; a.obj = gp->dObjB; a.res = gp->dResB;
+        a.X = gp->dX; a.XT = gp->dXT; a.Y = gp->dY; a.theta = gp->dThetaB; a.obj = gp->dObjB; a.res = gp->dResB;
         a.N = N; a.Npad = Npad; a.d = d; a.want_grad = want_grad ? 1 : 0;
         a.clk = nullptr;
         static const bool stamp = getenv("AOED_FIT_STAMP") != nullptr;  // tuning aid: prints per-phase cycles of problem 0

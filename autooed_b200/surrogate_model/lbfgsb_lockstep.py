@@ -63,6 +63,7 @@ class _Run:
         self.dsave = np.zeros(29, dtype=np.float64)
         self.nfev = self.nit = 0
         self.done = False
+        self._x_eval = self._f_eval = self._g_eval = None
 
     def advance(self):
         """Runs the optimiser until it asks for f, g at `self.x` (returns True) or stops (returns False)."""
@@ -71,6 +72,11 @@ class _Run:
             setulb(_MAXCOR, self.x, self.low, self.up, self.nbd, self.f, self.g, _FACTR, _GTOL, self.wa, self.iwa,
                    self.task, self.lsave, self.isave, self.dsave, _MAXLS, self.ln_task)
             if self.task[0] == _TASK_FG:
+                # scipy's ScalarFunction re-uses f and g when the routine asks again at the point it evaluated last (it can,
+                # after a line-search restart) and does not count that as an evaluation: same here
+                if self._x_eval is not None and np.array_equal(self.x, self._x_eval):
+                    self.f, self.g = self._f_eval, self._g_eval.copy()
+                    continue
                 return True
             if self.task[0] == _TASK_NEW_X:
                 self.nit += 1
@@ -84,6 +90,7 @@ class _Run:
 
     def feed(self, f, g):
         self.f, self.g = float(f), np.array(g, dtype=np.float64)  # own contiguous float64 copy
+        self._x_eval, self._f_eval, self._g_eval = self.x.copy(), self.f, self.g.copy()
         self.nfev += 1
 
 
