@@ -78,7 +78,9 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
                       double* h_lml, double* h_grad /* may be NULL */);
 
 /* replaces the tail of GaussianProcessRegressor.fit (_gpr.py:349-367): fixes theta (n_obj x p), factorises
- * K = k(X,X) + 1e-10 I, computes alpha_ and caches L^-1 for the posterior.  AOED_ERR_NOT_PD on failure. */
+ * K = k(X,X) + 1e-10 I for all objectives in ONE batch of the library's own blocked Cholesky + triangular inverse
+ * (FP64 DMMA tile GEMMs, csrc/blocked.cu — no cuSOLVER / cuBLAS), computes alpha_ and caches L^-1 for the posterior.
+ * AOED_ERR_NOT_PD on failure. */
 int aoed_gp_set_theta(aoed_gp_t* gp, const double* h_theta);
 
 /* sklearn attributes other AutoOED modules read (`gp.L_`, `gp.alpha_`, `log_marginal_likelihood_value_`):
@@ -115,7 +117,7 @@ int aoed_gp_get_counters(aoed_gp_t* gp, int64_t* n_launches, double* trmm_ms, in
                          double* trmm_flops);
 int aoed_gp_reset_counters(aoed_gp_t* gp);
 /* how many log-marginal-likelihood problems each device path served: the one-CTA-per-problem shared-memory kernel
- * (n_train <= 232) and the blocked multi-stream path. */
+ * (n_train <= 232) and the batched blocked factorisation (csrc/blocked.cu: every launch covers all problems of the call). */
 int aoed_gp_get_fit_counters(aoed_gp_t* gp, int64_t* n_small, int64_t* n_blocked);
 
 /* ---- NSGA-II on the device -----------------------------------------------------------
@@ -173,7 +175,11 @@ int aoed_pareto_rank(int device, int64_t n, int m, const double* h_Y, int32_t* h
  * n_front x m), reference point h_ref (m).  Strict '>' so the lowest index wins ties (hvi.py:35-37);
  * when no candidate has a positive contribution the entry is -1 and the caller draws the random fallback
  * (hvi.py:38-39) with the host RNG, then calls again with the updated front (see selection/hvi.py in the
- * Python package).  h_contrib (batch) receives the winning contributions (may be NULL). */
+ * Python package).  h_contrib (batch) receives the winning contributions (may be NULL).
+ * All rounds run on the device without host synchronisation (candidates, front and taken mask resident, one kernel per
+ * round); a round whose two best contributions differ by <= 1e-12 (HV(front) + best) — or in which nothing is positive — is
+ * re-decided on the host in the reference's own form HV(front + y) - HV(front) (hvi.py:28-37), pymoo's non-dominated
+ * pre-filter included.  n_obj <= 6, n_obj * (n_front + batch) <= 25600. */
 int aoed_hvi_select(int device, int64_t n_cand, int m, const double* h_Yc, int64_t n_front,
                     const double* h_front, const double* h_ref, int batch, const uint8_t* h_excluded,
                     int64_t* h_idx, double* h_contrib);
