@@ -153,108 +153,87 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_blk_kernel(LmlSmallArgs p) 
     FB_STAMP(1)
 
     // ---- 2: blocked Cholesky; the diagonal blocks end up holding L_kk^-1 ------------------------------------------
-    for (int kb = 0; kb < nblk; ++kb) {
+    // The sequential chain (one warp factoring the 16 x 16 diagonal block in registers, pivot column passed around by
+    // shuffles) is the only thing left on the critical path: the panel below it is a triangular SOLVE with one row per
+    // thread instead of "invert the block, then multiply"; with look-ahead warp 0 updates block (kb+1, kb+1) right after
+    // the panel and factors it while warps 1..15 finish the trailing update; the 16 x 16 inverses that phase 3 starts
+    // from are formed afterwards, all blocks at once.  zv serves as the table of 1 / L_cc until phase 4 needs it.
+    double* ipv = zv;
+    auto factor_diag = [&](int kb) {
         const int k0 = kb * FB;
-        if (warp == 0) {
-            const long long tdiag0 = (p.clk != nullptr) ? clock64() : 0;
-            // diagonal block (lower; identity padding beyond N): unblocked Cholesky with row r of the block in the
-            // registers of lane r (lanes 16..31 mirror 0..15) and the pivot column passed around by shuffles — the chain
-            // per pivot is one shuffle, one rsqrt, one multiply, one shuffle, one FMA instead of three shared-memory
-            // round trips.  Same operations in the same order as the shared-memory version it replaces.  Then -> Dsm for
-            // the inverse below.
-            const int r = lane & 15;
-            double a[FB];
+        const long long tdiag0 = (p.clk != nullptr) ? clock64() : 0;
+        const int r = lane & 15;
+        double a[FB];
 #pragma unroll
-            for (int c = 0; c < FB; ++c) {
-                double v = 0.0;
-                if (c <= r) v = (k0 + r < N) ? Lp[tri(k0 + r) + k0 + c] : (r == c ? 1.0 : 0.0);
-                a[c] = v;
-            }
-            bool bad = false;
+        for (int c = 0; c < FB; ++c) {
+            double v = 0.0;
+            if (c <= r) v = (k0 + r < N) ? Lp[tri(k0 + r) + k0 + c] : (r == c ? 1.0 : 0.0);  // identity padding beyond N
+            a[c] = v;
+        }
+        bool bad = false;
 #pragma unroll
-            for (int c = 0; c < FB; ++c) {
-                if (!bad) {
-                    const double dcc = __shfl_sync(0xffffffffu, a[c], c);
-                    if (!(dcc > 0.0)) {
-                        bad = true;  // the same value in every lane: uniform
-                    } else {
-                        const double ip = rsqrt(dcc);
-                        a[c] = (r == c) ? dcc * ip : a[c] * ip;  // L_rc (rows above the pivot hold 0)
-                        if (lane == c) Dinv[c * (FB + 1) + c] = ip;  // 1 / L_cc
+        for (int c = 0; c < FB; ++c) {
+            if (!bad) {
+                const double dcc = __shfl_sync(0xffffffffu, a[c], c);
+                if (!(dcc > 0.0)) {
+                    bad = true;  // the same value in every lane: uniform
+                } else {
+                    const double ip = rsqrt(dcc);
+                    a[c] = (r == c) ? dcc * ip : a[c] * ip;  // L_rc (rows above the pivot hold 0)
+                    if (lane == c) {
+                        Dinv[c * (FB + 1) + c] = ip;  // 1 / L_cc for the panel solve
+                        if (k0 + c < N) ipv[k0 + c] = ip;
+                    }
 #pragma unroll
-                        for (int cc = c + 1; cc < FB; ++cc) {
-                            const double lcc = __shfl_sync(0xffffffffu, a[c], cc);  // L_{cc,c}
-                            if (cc <= r) a[cc] = fma(-a[c], lcc, a[cc]);
-                        }
+                    for (int cc = c + 1; cc < FB; ++cc) {
+                        const double lcc = __shfl_sync(0xffffffffu, a[c], cc);  // L_{cc,c}
+                        if (cc <= r) a[cc] = fma(-a[c], lcc, a[cc]);
                     }
                 }
             }
-            if (lane < FB) {
+        }
+        if (bad) {
+            if (lane == 0) s_fail = 1;
+        } else if (lane < FB) {
 #pragma unroll
-                for (int c = 0; c < FB; ++c) Dsm[lane * (FB + 1) + c] = a[c];
+            for (int c = 0; c < FB; ++c) {
+                Dsm[lane * (FB + 1) + c] = a[c];
+                if (c <= lane && k0 + lane < N) Lp[tri(k0 + lane) + k0 + c] = a[c];
             }
-            __syncwarp();
-            const long long tdiag1 = (p.clk != nullptr) ? clock64() : 0;
-            if (p.clk != nullptr && lane == 0) p.clk[int64_t(b) * 8 + 6] = (kb == 0 ? 0 : p.clk[int64_t(b) * 8 + 6]) + (tdiag1 - tdiag0);
-            if (bad) {
-                if (lane == 0) s_fail = 1;
-            } else {
-                if (lane < FB && k0 + lane < N) dg[k0 + lane] = Dsm[lane * (FB + 1) + lane];
-                // inverse of the lower-triangular block, one column per lane (forward substitution in registers)
-                if (lane < FB) {
-                    const int j = lane;
-                    double x[FB];
+            if (k0 + lane < N) dg[k0 + lane] = a[lane];
+        }
+        if (p.clk != nullptr && lane == 0) p.clk[int64_t(b) * 8 + 6] = (kb == 0 ? 0 : p.clk[int64_t(b) * 8 + 6]) + (clock64() - tdiag0);
+    };
+    if (warp == 0) factor_diag(0);
+    __syncthreads();
+    for (int kb = 0; kb < nblk && !s_fail; ++kb) {
+        const int k0 = kb * FB;
+        // panel: L[i][kb-block] = A[i][kb-block] L_kk^-T by substitution, one row per thread; also into the panel buffer
+        {
+            const int i = k0 + FB + tid;
+            if (i < Nr) {
+                double x[FB];
 #pragma unroll
-                    for (int i = 0; i < FB; ++i) x[i] = 0.0;
+                for (int c = 0; c < FB; ++c) {
+                    double sacc = LP(i, k0 + c);
 #pragma unroll
-                    for (int i = 0; i < FB; ++i) {
-                        if (i < j) continue;
-                        const double idiag = Dinv[i * (FB + 1) + i];
-                        if (i == j) {
-                            x[i] = idiag;
-                        } else {
-                            double s = 0.0;
-#pragma unroll
-                            for (int k = 0; k < FB; ++k)
-                                if (k >= j && k < i) s = fma(Dsm[i * (FB + 1) + k], x[k], s);
-                            x[i] = -s * idiag;
-                        }
-                    }
-                    __syncwarp(0xffff);
-#pragma unroll
-                    for (int i = 0; i < FB; ++i) Dinv[i * (FB + 1) + j] = x[i];  // upper part = 0
+                    for (int j = 0; j < c; ++j) sacc = fma(-x[j], Dsm[c * (FB + 1) + j], sacc);
+                    x[c] = sacc * Dinv[c * (FB + 1) + c];
                 }
-                __syncwarp();
-                // the diagonal block of the packed matrix now stores L_kk^-1 (phase 3 needs only that)
-                for (int e = lane; e < FB * FB; e += 32) {
-                    const int r = e / FB, c = e % FB;
-                    if (c <= r && k0 + r < N) Lp[tri(k0 + r) + k0 + c] = Dinv[r * (FB + 1) + c];
+#pragma unroll
+                for (int c = 0; c < FB; ++c) {
+                    const bool in = i < N && k0 + c < N;
+                    if (in) Lp[tri(i) + k0 + c] = x[c];
+                    P[i * FBP + c] = in ? x[c] : 0.0;
                 }
             }
-            if (p.clk != nullptr && lane == 0)
-                p.clk[int64_t(b) * 8 + 7] = (kb == 0 ? 0 : p.clk[int64_t(b) * 8 + 7]) + (clock64() - tdiag1);
         }
         __syncthreads();
-        if (s_fail) break;
-        // panel: L[ib][kb] = A[ib][kb] * Dinv^T for the row blocks below, one block per warp; copy into colP as well
-        for (int ib = kb + 1 + warp; ib < nblk; ib += FS_WARPS) {
-            const int i0 = ib * FB;
-            BlkAcc acc;
-            acc.zero();
-            blk_mma(acc, [&](int r, int k) { return LP(i0 + r, k0 + k); },
-                    [&](int k, int n) { return Dinv[n * (FB + 1) + k]; }, g, q);
-            __syncwarp();
-            blk_foreach(acc, [&](int r, int c, double& v) {
-                if (i0 + r < N && k0 + c < N) Lp[tri(i0 + r) + k0 + c] = v;
-                P[(i0 + r) * FBP + c] = (i0 + r < N && k0 + c < N) ? v : 0.0;
-            }, g, q);
-        }
-        __syncthreads();
-        // trailing update: A[ib][jb] -= L[ib][kb] L[jb][kb]^T for kb < jb <= ib
+        // trailing update: A[ib][jb] -= L[ib][kb] L[jb][kb]^T for kb < jb <= ib; pair 0 is the next diagonal block
         {
             const int nt = nblk - kb - 1;
             const int npair = nt * (nt + 1) / 2;
-            for (int pr = warp; pr < npair; pr += FS_WARPS) {
+            auto do_pair = [&](int pr) {
                 int bi = int((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
                 while (bi * (bi + 1) / 2 > pr) --bi;
                 while ((bi + 1) * (bi + 2) / 2 <= pr) ++bi;
@@ -268,9 +247,53 @@ __global__ void __launch_bounds__(FS_THREADS, 1) lml_blk_kernel(LmlSmallArgs p) 
                     const int i = i0 + r, j = j0 + c;
                     if (i < N && j <= i) Lp[tri(i) + j] -= v;
                 }, g, q);
+            };
+            if (warp == 0) {
+                if (npair > 0) {
+                    do_pair(0);
+                    __syncwarp();
+                    factor_diag(kb + 1);  // overwrites Dsm / Dinv: the panel solve of step kb is behind the barrier above
+                }
+            } else {
+                for (int pr = warp; pr < npair; pr += FS_WARPS - 1) do_pair(pr);
             }
         }
         __syncthreads();
+    }
+    // inverses of all diagonal blocks, one warp per block, one column per lane (forward substitution in registers)
+    if (!s_fail) {
+        const long long tinv0 = (p.clk != nullptr) ? clock64() : 0;
+        for (int kb = warp; kb < nblk; kb += FS_WARPS) {
+            const int k0 = kb * FB;
+            double x[FB];
+            const int j = lane & 15;
+            auto Lkk = [&](int i, int k) -> double {  // the factored block with its identity padding
+                return (k0 + i < N) ? Lp[tri(k0 + i) + k0 + k] : (i == k ? 1.0 : 0.0);
+            };
+#pragma unroll
+            for (int i = 0; i < FB; ++i) x[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < FB; ++i) {
+                if (i < j) continue;
+                const double idiag = (k0 + i < N) ? ipv[k0 + i] : 1.0;
+                if (i == j) {
+                    x[i] = idiag;
+                } else {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < FB; ++k)
+                        if (k >= j && k < i) sacc = fma(Lkk(i, k), x[k], sacc);
+                    x[i] = -sacc * idiag;
+                }
+            }
+            __syncwarp();  // every lane has read the block before anybody overwrites it
+            if (lane < FB) {
+#pragma unroll
+                for (int i = 0; i < FB; ++i)
+                    if (i >= j && k0 + i < N) Lp[tri(k0 + i) + k0 + j] = x[i];
+            }
+        }
+        if (p.clk != nullptr && tid == 0) p.clk[int64_t(b) * 8 + 7] = clock64() - tinv0;
     }
     __syncthreads();
     double* out = p.res + int64_t(b) * (d + 3);

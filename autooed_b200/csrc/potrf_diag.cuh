@@ -2,10 +2,10 @@
 // diagonal tile  A_kk = L_kk L_kk^T  in shared memory and inverts the factor, so that the panel below it becomes a GEMM
 // (L_ik = A_ik L_kk^-T, tgemm_kernel<NT>) and the triangular inverse of the whole matrix can start from X_kk = L_kk^-1.
 //
-// Inside the tile the algorithm is the blocked right-looking one of lml_blk_kernel (fit_small2.cuh) on 16 x 16
-// sub-blocks: the diagonal sub-block is factored by one warp in registers with shuffles and inverted by forward
-// substitution, panel and trailing update run as DMMA block products on all 16 warps; then X = L^-1 in place, block
-// row by block row.  The tile is stored as a full square (row length 132: every DMMA fragment load below is
+// Inside the tile: blocked right-looking Cholesky on 16 x 16 sub-blocks — the diagonal sub-block is factored by one warp
+// in registers with shuffles (the only sequential chain; look-ahead keeps it busy), the panel below is a triangular solve
+// with one row per thread, the trailing update runs as DMMA block products; then the eight 16 x 16 inverses at once and
+// X = L^-1 in place, block row by block row.  The tile is stored as a full square (row length 132: every DMMA fragment load below is
 // bank-conflict free), the strictly upper sub-blocks hold transposed copies of the panels so that the in-place
 // inverse reads L[ib][kb] from there while the lower sub-block is being overwritten.
 //
@@ -20,7 +20,7 @@ namespace aoed {
 
 constexpr int PD_N = 128, PD_LD = 132, PD_NB = PD_N / FB;
 constexpr int PD_THREADS = 512, PD_WARPS = PD_THREADS / 32;
-constexpr size_t PD_SMEM = (size_t(PD_N) * PD_LD + 2 * FB * (FB + 1)) * sizeof(double);
+constexpr size_t PD_SMEM = (size_t(PD_N) * PD_LD + PD_NB * FB * (FB + 1) + PD_N) * sizeof(double);
 
 struct PotrfDiagArgs {
     double* K;       // [batch][Npad][ld]: tile (k, k) is read, L_kk written back
@@ -34,8 +34,8 @@ struct PotrfDiagArgs {
 __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(PotrfDiagArgs p) {
     extern __shared__ __align__(16) double pd_smem[];
     double* S = pd_smem;                     // [128][132]
-    double* Dsm = S + size_t(PD_N) * PD_LD;  // [16][17] diagonal sub-block
-    double* Dinv = Dsm + FB * (FB + 1);      // [16][17] its inverse
+    double* Lsm = S + size_t(PD_N) * PD_LD;      // [8][16][17] the factored diagonal sub-blocks
+    double* ipv = Lsm + PD_NB * FB * (FB + 1);   // [128] 1 / L_cc
     __shared__ int s_fail;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -64,97 +64,83 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(PotrfDiagArgs
     }
     __syncthreads();
 
-    // ---- blocked Cholesky; the diagonal sub-blocks end up holding their inverses ------------------------------------
-    for (int kb = 0; kb < PD_NB; ++kb) {
+    // ---- blocked Cholesky ---------------------------------------------------------------------------------------------
+    // The sequential chain belongs to warp 0: it factors the 16 x 16 diagonal sub-block in registers (row r in lane r, pivot
+    // column passed around by shuffles).  Nothing else sits on that chain any more:
+    //   * the panel below is a triangular SOLVE, one row per thread (112 rows in parallel, 16 short dot products each),
+    //     instead of "invert the sub-block, then multiply";
+    //   * with look-ahead — after the panel, warp 0 updates only sub-block (kb+1, kb+1) and factors it straight away while
+    //     warps 1..15 do the rest of the trailing update;
+    //   * the 16 x 16 inverses the in-place inversion below starts from are formed afterwards, all eight at once.
+    auto factor_diag = [&](int kb) {
         const int k0 = kb * FB;
-        if (warp == 0) {
-            // row r of the sub-block in the registers of lane r (lanes 16..31 mirror 0..15), pivot column by shuffles
-            const int r = lane & 15;
-            double a[FB];
+        const int r = lane & 15;
+        double a[FB];
 #pragma unroll
-            for (int c = 0; c < FB; ++c) a[c] = (c <= r) ? S[(k0 + r) * PD_LD + k0 + c] : 0.0;
-            int bad = 0;
+        for (int c = 0; c < FB; ++c) a[c] = (c <= r) ? S[(k0 + r) * PD_LD + k0 + c] : 0.0;
+        int bad = 0;
+#pragma unroll
+        for (int c = 0; c < FB; ++c) {
+            if (!bad) {
+                const double dcc = __shfl_sync(0xffffffffu, a[c], c);
+                if (!(dcc > 0.0)) {
+                    bad = c + 1;  // the same value in every lane: uniform
+                } else {
+                    const double ip = rsqrt(dcc);
+                    a[c] = (r == c) ? dcc * ip : a[c] * ip;
+                    if (lane == c) ipv[k0 + c] = ip;
+#pragma unroll
+                    for (int cc = c + 1; cc < FB; ++cc) {
+                        const double lcc = __shfl_sync(0xffffffffu, a[c], cc);
+                        if (cc <= r) a[cc] = fma(-a[c], lcc, a[cc]);
+                    }
+                }
+            }
+        }
+        if (bad) {
+            if (lane == 0) s_fail = p.k * PD_N + k0 + bad;
+            return;
+        }
+        if (lane < FB) {
+            double* Lk = Lsm + kb * FB * (FB + 1);
 #pragma unroll
             for (int c = 0; c < FB; ++c) {
-                if (!bad) {
-                    const double dcc = __shfl_sync(0xffffffffu, a[c], c);
-                    if (!(dcc > 0.0)) {
-                        bad = c + 1;  // the same value in every lane: uniform
-                    } else {
-                        const double ip = rsqrt(dcc);
-                        a[c] = (r == c) ? dcc * ip : a[c] * ip;
-                        if (lane == c) Dinv[c * (FB + 1) + c] = ip;
-#pragma unroll
-                        for (int cc = c + 1; cc < FB; ++cc) {
-                            const double lcc = __shfl_sync(0xffffffffu, a[c], cc);
-                            if (cc <= r) a[cc] = fma(-a[c], lcc, a[cc]);
-                        }
-                    }
-                }
+                Lk[lane * (FB + 1) + c] = a[c];
+                Kt[int64_t(k0 + lane) * ld + k0 + c] = a[c];  // L sub-block (zeros above the diagonal)
             }
-            if (bad) {
-                if (lane == 0) s_fail = p.k * PD_N + k0 + bad;
-            } else {
-                if (lane < FB) {
+        }
+    };
+    if (warp == 0) factor_diag(0);
+    __syncthreads();
+    for (int kb = 0; kb < PD_NB && !s_fail; ++kb) {
+        const int k0 = kb * FB;
+        // panel: L[i][kb-block] = A[i][kb-block] L_kk^-T, one row per thread by substitution; also kept transposed in the
+        // upper sub-blocks [kb][ib]
+        {
+            const int i = k0 + FB + tid;
+            if (i < PD_N) {
+                const double* Lk = Lsm + kb * FB * (FB + 1);
+                double x[FB];
 #pragma unroll
-                    for (int c = 0; c < FB; ++c) {
-                        Dsm[lane * (FB + 1) + c] = a[c];
-                        Kt[int64_t(k0 + lane) * ld + k0 + c] = a[c];  // L sub-block (zeros above the diagonal)
-                    }
+                for (int c = 0; c < FB; ++c) {
+                    double sacc = S[i * PD_LD + k0 + c];
+#pragma unroll
+                    for (int j = 0; j < c; ++j) sacc = fma(-x[j], Lk[c * (FB + 1) + j], sacc);
+                    x[c] = sacc * ipv[k0 + c];
                 }
-                __syncwarp();
-                // inverse of the lower-triangular sub-block, one column per lane (forward substitution in registers)
-                if (lane < FB) {
-                    const int j = lane;
-                    double x[FB];
 #pragma unroll
-                    for (int i = 0; i < FB; ++i) x[i] = 0.0;
-#pragma unroll
-                    for (int i = 0; i < FB; ++i) {
-                        if (i < j) continue;
-                        const double idiag = Dinv[i * (FB + 1) + i];
-                        if (i == j) {
-                            x[i] = idiag;
-                        } else {
-                            double s = 0.0;
-#pragma unroll
-                            for (int k = 0; k < FB; ++k)
-                                if (k >= j && k < i) s = fma(Dsm[i * (FB + 1) + k], x[k], s);
-                            x[i] = -s * idiag;
-                        }
-                    }
-                    __syncwarp(0xffff);
-#pragma unroll
-                    for (int i = 0; i < FB; ++i) Dinv[i * (FB + 1) + j] = x[i];  // upper part = 0
-                }
-                __syncwarp();
-                for (int e = lane; e < FB * FB; e += 32) {
-                    const int rr = e / FB, c = e % FB;
-                    S[(k0 + rr) * PD_LD + k0 + c] = Dinv[rr * (FB + 1) + c];
+                for (int c = 0; c < FB; ++c) {
+                    S[i * PD_LD + k0 + c] = x[c];
+                    S[(k0 + c) * PD_LD + i] = x[c];
                 }
             }
         }
         __syncthreads();
-        if (s_fail) break;
-        // panel: L[ib][kb] = A[ib][kb] * Dinv^T; also kept transposed in the upper sub-block [kb][ib]
-        for (int ib = kb + 1 + warp; ib < PD_NB; ib += PD_WARPS) {
-            const int i0 = ib * FB;
-            BlkAcc acc;
-            acc.zero();
-            blk_mma(acc, [&](int r, int k) { return S[(i0 + r) * PD_LD + k0 + k]; },
-                    [&](int k, int n) { return Dinv[n * (FB + 1) + k]; }, g, q);
-            __syncwarp();
-            blk_foreach(acc, [&](int r, int c, double& v) {
-                S[(i0 + r) * PD_LD + k0 + c] = v;
-                S[(k0 + c) * PD_LD + i0 + r] = v;
-            }, g, q);
-        }
-        __syncthreads();
-        // trailing update: A[ib][jb] -= L[ib][kb] L[jb][kb]^T for kb < jb <= ib
+        // trailing update: A[ib][jb] -= L[ib][kb] L[jb][kb]^T for kb < jb <= ib.  Pair 0 is the next diagonal sub-block
         {
             const int nt = PD_NB - kb - 1;
             const int npair = nt * (nt + 1) / 2;
-            for (int pr = warp; pr < npair; pr += PD_WARPS) {
+            auto do_pair = [&](int pr) {
                 int bi = 0;
                 while ((bi + 1) * (bi + 2) / 2 <= pr) ++bi;
                 const int bj = pr - bi * (bi + 1) / 2;
@@ -166,6 +152,15 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(PotrfDiagArgs
                 blk_foreach(acc, [&](int r, int c, double& v) {
                     if (j0 + c <= i0 + r) S[(i0 + r) * PD_LD + j0 + c] -= v;
                 }, g, q);
+            };
+            if (warp == 0) {
+                if (npair > 0) {
+                    do_pair(0);
+                    __syncwarp();
+                    factor_diag(kb + 1);
+                }
+            } else {
+                for (int pr = warp; pr < npair; pr += PD_WARPS - 1) do_pair(pr);
             }
         }
         __syncthreads();
@@ -180,6 +175,31 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(PotrfDiagArgs
         const int r = e >> 7, c = e & 127;
         if ((r >> 4) == (c >> 4)) continue;
         Kt[int64_t(r) * ld + c] = (c < r) ? S[r * PD_LD + c] : 0.0;
+    }
+    // inverses of the eight diagonal sub-blocks, one warp each, one column per lane (forward substitution in registers):
+    // the in-place inversion below starts from them
+    if (warp < PD_NB && lane < FB) {
+        const int k0 = warp * FB, j = lane;
+        const double* Lk = Lsm + warp * FB * (FB + 1);
+        double x[FB];
+#pragma unroll
+        for (int i = 0; i < FB; ++i) x[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < FB; ++i) {
+            if (i < j) continue;
+            const double idiag = ipv[k0 + i];
+            if (i == j) {
+                x[i] = idiag;
+            } else {
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = 0; k < FB; ++k)
+                    if (k >= j && k < i) sacc = fma(Lk[i * (FB + 1) + k], x[k], sacc);
+                x[i] = -sacc * idiag;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < FB; ++i) S[(k0 + i) * PD_LD + k0 + j] = x[i];  // zeros above the diagonal
     }
     __syncthreads();
 
