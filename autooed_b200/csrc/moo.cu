@@ -302,6 +302,7 @@ struct HviArgs {
 };
 
 constexpr int HVI_THREADS = 128;
+constexpr int HVI_UNROLL = 4;
 
 __device__ __forceinline__ Top2 block_top2(Top2 t, Top2* sm) {
     sm[threadIdx.x] = t;
@@ -333,28 +334,48 @@ __global__ void __launch_bounds__(HVI_THREADS) hvi_round_kernel(HviArgs a) {
     Top2 t;
     t.v1 = t.v2 = -1.0;
     t.i1 = t.i2 = 0x7fffffffffffffffLL;
-    for (long long i = blockIdx.x * (long long)HVI_THREADS + threadIdx.x; i < a.n; i += (long long)gridDim.x * HVI_THREADS) {
-        double y[M], lev[M];
-        bool inside = true;
+    // HVI_UNROLL candidates per thread and step: their loads (8 m bytes + the taken flag each) are issued together — the scan is
+    // bound by memory latency, not by the few dozen instructions of a dominated candidate's sweep
+    const long long stride = (long long)gridDim.x * HVI_THREADS;
+    for (long long i0 = blockIdx.x * (long long)HVI_THREADS + threadIdx.x; i0 < a.n; i0 += HVI_UNROLL * stride) {
+        double yy[HVI_UNROLL][M];
+        uint8_t ex[HVI_UNROLL];
 #pragma unroll
-        for (int c = 0; c < M; ++c) {
-            y[c] = a.YcT[c * a.n + i];
-            lev[c] = y[c];
-            inside = inside && (y[c] <= sref[c]);
-        }
-        double v = 0.0;
-        if (inside && !a.excluded[i]) {
-            if (M == 1) {
-                double best = sref[0];
-                for (int j = 0; j < k; ++j) best = fmin(best, sfront[j]);
-                v = fmax(0.0, best - y[0]);
-            } else {
-                v = Excl<M, M>::run(y, sfront, k, sref, lev);
+        for (int u = 0; u < HVI_UNROLL; ++u) {
+            const long long i = i0 + u * stride;
+            ex[u] = 1;
+            if (i < a.n) {
+                ex[u] = a.excluded[i];
+#pragma unroll
+                for (int c = 0; c < M; ++c) yy[u][c] = a.YcT[c * a.n + i];
             }
-            // contributions only shrink as the front grows: a candidate at zero stays at zero and is skipped from now on
-            if (!(v > 0.0)) a.excluded[i] = 2;
         }
-        top_push(t, v, i);
+#pragma unroll
+        for (int u = 0; u < HVI_UNROLL; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= a.n) break;
+            double y[M], lev[M];
+            bool inside = true;
+#pragma unroll
+            for (int c = 0; c < M; ++c) {
+                y[c] = yy[u][c];
+                lev[c] = y[c];
+                inside = inside && (y[c] <= sref[c]);
+            }
+            double v = 0.0;
+            if (inside && !ex[u]) {
+                if (M == 1) {
+                    double best = sref[0];
+                    for (int j = 0; j < k; ++j) best = fmin(best, sfront[j]);
+                    v = fmax(0.0, best - y[0]);
+                } else {
+                    v = Excl<M, M>::run(y, sfront, k, sref, lev);
+                }
+                // contributions only shrink as the front grows: a candidate at zero stays at zero and is skipped from now on
+                if (!(v > 0.0)) a.excluded[i] = 2;
+            }
+            top_push(t, v, i);
+        }
     }
     t = block_top2(t, stop);
     if (threadIdx.x == 0) {

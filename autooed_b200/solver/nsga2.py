@@ -256,6 +256,11 @@ class NSGA2(Solver):
             Xc, Fc, self.n_eval = device_nsga2(self.problem.acquisition, X, self.problem.xl, self.problem.xu,
                                                self.algo.pop_size, self.n_gen, seed)
             return Xc, Fc
+        if self.algo.rank_fn is _default_rank:  # non-dominated sorting on the GPU the surrogate lives on
+            from functools import partial
+            from autooed_b200.utils.pareto import pareto_rank
+            sm = getattr(self.problem.acquisition, 'surrogate_model', None)
+            self.algo.rank_fn = partial(pareto_rank, device=getattr(sm, 'device', 0))
         out = self.algo.minimize(self.problem, X, self.n_gen)
         self.n_eval = self.algo.n_eval
         return out

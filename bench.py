@@ -605,7 +605,7 @@ def run_fit_mode(args):
             print(json.dumps({"mode": "fit", "what": "lml+grad batch", "N": N, "d": d, "nu": nu, "problems": B,
                               "ms_per_batch": 1e3 * dt, "problems_per_s": B / dt, "cpu_port_ms_per_problem": 1e3 * cpu_s,
                               "cpu_threads": threads, "speedup_vs_cpu_serial": cpu_s * B / dt,
-                              "path": "shared-memory kernel" if N <= 232 else "blocked multi-stream"}), flush=True)
+                              "path": "one-CTA shared-memory kernel" if N <= 232 else "batched blocked factorisation (tgemm / potrf_diag)"}), flush=True)
 
     def full_fit(N, d, m, nu, n_restarts):
         X, Y = _fit_data(N, d, m)
@@ -752,12 +752,15 @@ def run_mobo_mode(args):
     from autooed_b200.utils.pareto import calc_hypervolume
     from oracle import moo_oracle as mo
     ctx, threads = blas_threads()
+    # both arms run the SAME number of iterations from the same seed (the training set grows by `batch` per iteration, so
+    # iteration counts must match for the per-iteration times to be comparable); --mobo-iters bounds the CPU arm's minutes
+    it1, it2 = min(args.mobo_iters, 6), max(2, min(args.mobo_iters // 3, 3))
     configs = [dict(name="tsemo-default", f=_zdt1, d=6, m=2, nu=1, acq="ts", pop=200, gens=200, batch=10, n_init=20,
-                    iters=args.mobo_iters, cpu_iters=min(args.mobo_iters, 3)),
+                    iters=it1, cpu_iters=it1),
                dict(name="c1", f=_zdt1, d=6, m=2, nu=1, acq="identity", pop=200, gens=200, batch=10, n_init=20,
-                    iters=args.mobo_iters, cpu_iters=min(args.mobo_iters, 3)),
+                    iters=it1, cpu_iters=it1),
                dict(name="c2", f=lambda X: _dtlz2(X, 3), d=10, m=3, nu=1, acq="ei", pop=1000, gens=200, batch=20, n_init=30,
-                    iters=max(2, args.mobo_iters // 4), cpu_iters=1)]
+                    iters=it2, cpu_iters=it2)]
     for c in configs:
         prob = SimpleProblem(c["d"], c["m"])
         for arm in ("b200", "cpu_port"):
