@@ -251,7 +251,9 @@ int launch_hvc(int m, const double* YcT, int64_t n, const double* front, int k, 
         HVC_CASE(4)
         HVC_CASE(5)
         HVC_CASE(6)
-        default: return mfail(AOED_ERR_UNSUPPORTED, "hypervolume improvement supports n_obj <= 6");
+        HVC_CASE(7)
+        HVC_CASE(8)
+        default: return mfail(AOED_ERR_UNSUPPORTED, "hypervolume improvement supports n_obj <= 8");
     }
 #undef HVC_CASE
     MCU(cudaGetLastError());
@@ -439,8 +441,8 @@ int launch_hvi_round(int m, const HviArgs& a, int grid, size_t smem, cudaStream_
         hvi_round_kernel<MM><<<grid, HVI_THREADS, smem, s>>>(a);                                                          \
         break;
     switch (m) {
-        HVR_CASE(1) HVR_CASE(2) HVR_CASE(3) HVR_CASE(4) HVR_CASE(5) HVR_CASE(6)
-        default: return mfail(AOED_ERR_UNSUPPORTED, "hypervolume improvement supports n_obj <= 6");
+        HVR_CASE(1) HVR_CASE(2) HVR_CASE(3) HVR_CASE(4) HVR_CASE(5) HVR_CASE(6) HVR_CASE(7) HVR_CASE(8)
+        default: return mfail(AOED_ERR_UNSUPPORTED, "hypervolume improvement supports n_obj <= 8");
     }
 #undef HVR_CASE
     MCU(cudaGetLastError());
@@ -823,7 +825,7 @@ int aoed_hvi_select(int device, int64_t n_cand, int m, const double* h_Yc, int64
         if (h_contrib) h_contrib[b] = 0.0;
     }
     if (n_cand == 0 || batch == 0) return AOED_OK;
-    if (m > 6) return mfail(AOED_ERR_UNSUPPORTED, "hypervolume improvement supports n_obj <= 6");
+    if (m > 8) return mfail(AOED_ERR_UNSUPPORTED, "hypervolume improvement supports n_obj <= 8");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev || device < 0) return mfail(AOED_ERR_NO_DEVICE, "no CUDA device");
     aoed::DeviceGuard guard_(device);

@@ -179,7 +179,7 @@ int aoed_pareto_rank(int device, int64_t n, int m, const double* h_Y, int32_t* h
  * All rounds run on the device without host synchronisation (candidates, front and taken mask resident, one kernel per
  * round); a round whose two best contributions differ by <= 1e-12 (HV(front) + best) — or in which nothing is positive — is
  * re-decided on the host in the reference's own form HV(front + y) - HV(front) (hvi.py:28-37), pymoo's non-dominated
- * pre-filter included.  n_obj <= 6, n_obj * (n_front + batch) <= 25600. */
+ * pre-filter included.  n_obj <= 8, n_obj * (n_front + batch) <= 25600. */
 int aoed_hvi_select(int device, int64_t n_cand, int m, const double* h_Yc, int64_t n_front,
                     const double* h_front, const double* h_ref, int batch, const uint8_t* h_excluded,
                     int64_t* h_idx, double* h_contrib);

@@ -86,7 +86,7 @@ def test_hv_contributions_vs_oracle(m):
     assert abs(pareto.calc_hypervolume(Y, ref) - base) < 1e-12 * max(1.0, base)
 
 
-@pytest.mark.parametrize("m,C,N,batch", [(2, 200, 40, 10), (3, 500, 60, 20), (2, 30, 200, 8), (4, 100, 30, 5)])
+@pytest.mark.parametrize("m,C,N,batch", [(2, 200, 40, 10), (3, 500, 60, 20), (2, 30, 200, 8), (4, 100, 30, 5), (7, 40, 20, 4), (8, 30, 15, 3)])
 def test_hvi_select_same_batch(m, C, N, batch):
     from autooed_b200.selection.hvi import hvi_select_indices
     rng = np.random.default_rng(100 * m + C)
