@@ -12,7 +12,9 @@ from oracle import penalize_oracle as po
 
 pytestmark = pytest.mark.gpu
 FILES = sorted(os.path.basename(f) for f in glob.glob(os.path.join(GOLDEN, "async_*.npz")))
-L_TOL = 2e-5  # stopping tolerance of the L-BFGS-B polish with numerical gradients (see tests/test_async_oracle.py)
+L_TOL = 5e-5  # the L-BFGS-B polish with numerical gradients (penalize.py:112-124) stops anywhere within its ftol of the steepest point:
+              # two implementations of the same model agree to ~2e-5 (tests/test_async_oracle.py), and last-bit changes of alpha
+              # (another factorisation order) move the stopping point by as much again
 
 
 def rel(a, b):
