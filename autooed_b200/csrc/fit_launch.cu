@@ -37,7 +37,9 @@ cudaError_t launch_small_dp(int DP, const LmlSmallArgs& a, int n_prob, cudaStrea
         case 24: return launch_small_one<NU, 24>(a, n_prob, sm, s);
         case 32: return launch_small_one<NU, 32>(a, n_prob, sm, s);
         case 48: return launch_small_one<NU, 48>(a, n_prob, sm, s);
-        default: return launch_small_one<NU, 64>(a, n_prob, sm, s);
+        case 64: return launch_small_one<NU, 64>(a, n_prob, sm, s);
+        case 96: return launch_small_one<NU, 96>(a, n_prob, sm, s);
+        default: return launch_small_one<NU, 128>(a, n_prob, sm, s);
     }
 }
 
@@ -50,7 +52,9 @@ cudaError_t launch_blk_dp(int DP, const LmlSmallArgs& a, int n_prob, cudaStream_
         case 24: return launch_blk_one<NU, 24>(a, n_prob, sm, s);
         case 32: return launch_blk_one<NU, 32>(a, n_prob, sm, s);
         case 48: return launch_blk_one<NU, 48>(a, n_prob, sm, s);
-        default: return launch_blk_one<NU, 64>(a, n_prob, sm, s);
+        case 64: return launch_blk_one<NU, 64>(a, n_prob, sm, s);
+        case 96: return launch_blk_one<NU, 96>(a, n_prob, sm, s);
+        default: return launch_blk_one<NU, 128>(a, n_prob, sm, s);
     }
 }
 

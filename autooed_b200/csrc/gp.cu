@@ -54,6 +54,8 @@ int pick_dp(int d) {
     if (d <= 32) return 32;
     if (d <= 48) return 48;
     if (d <= 64) return 64;
+    if (d <= 96) return 96;
+    if (d <= 128) return 128;
     return -1;
 }
 
@@ -269,7 +271,9 @@ void launch_xcov_any(int nu, int DP, int DE, const XcovArgs& a, dim3 grid, bool 
         case 3228: launch_xcov_nu<32, 28>(nu, a, grid, grad, s); break;
         case 3232: launch_xcov_nu<32, 32>(nu, a, grid, grad, s); break;
         case 4848: launch_xcov_nu<48, 48>(nu, a, grid, grad, s); break;
-        default: launch_xcov_nu<64, 64>(nu, a, grid, grad, s); break;
+        case 6464: launch_xcov_nu<64, 64>(nu, a, grid, grad, s); break;
+        case 9696: launch_xcov_nu<96, 96>(nu, a, grid, grad, s); break;
+        default: launch_xcov_nu<128, 128>(nu, a, grid, grad, s); break;
     }
 }
 
@@ -302,7 +306,9 @@ void query_occupancy(int nu, int DP, int DE, int& occ_xcov, int& occ_gradsum) {
         case 3228: occ_pair<32, 28>(nu, occ_xcov, occ_gradsum); break;
         case 3232: occ_pair<32, 32>(nu, occ_xcov, occ_gradsum); break;
         case 4848: occ_pair<48, 48>(nu, occ_xcov, occ_gradsum); break;
-        default: occ_pair<64, 64>(nu, occ_xcov, occ_gradsum); break;
+        case 6464: occ_pair<64, 64>(nu, occ_xcov, occ_gradsum); break;
+        case 9696: occ_pair<96, 96>(nu, occ_xcov, occ_gradsum); break;
+        default: occ_pair<128, 128>(nu, occ_xcov, occ_gradsum); break;
     }
 }
 
@@ -317,7 +323,9 @@ void launch_gradsum(int DP, int DE, const GradsumArgs& a, dim3 grid, cudaStream_
         case 3228: gradsum_kernel<32, 28><<<grid, XC_THREADS, 0, s>>>(a); break;
         case 3232: gradsum_kernel<32, 32><<<grid, XC_THREADS, 0, s>>>(a); break;
         case 4848: gradsum_kernel<48, 48><<<grid, XC_THREADS, 0, s>>>(a); break;
-        default: gradsum_kernel<64, 64><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 6464: gradsum_kernel<64, 64><<<grid, XC_THREADS, 0, s>>>(a); break;
+        case 9696: gradsum_kernel<96, 96><<<grid, XC_THREADS, 0, s>>>(a); break;
+        default: gradsum_kernel<128, 128><<<grid, XC_THREADS, 0, s>>>(a); break;
     }
 }
 
@@ -329,7 +337,9 @@ void launch_kmat_dp(int DP, const KmatArgs& a, dim3 grid, cudaStream_t s) {
         case 24: kmat_kernel<NU, 24><<<grid, 256, 0, s>>>(a); break;
         case 32: kmat_kernel<NU, 32><<<grid, 256, 0, s>>>(a); break;
         case 48: kmat_kernel<NU, 48><<<grid, 256, 0, s>>>(a); break;
-        default: kmat_kernel<NU, 64><<<grid, 256, 0, s>>>(a); break;
+        case 64: kmat_kernel<NU, 64><<<grid, 256, 0, s>>>(a); break;
+        case 96: kmat_kernel<NU, 96><<<grid, 256, 0, s>>>(a); break;
+        default: kmat_kernel<NU, 128><<<grid, 256, 0, s>>>(a); break;
     }
 }
 
@@ -350,7 +360,9 @@ void launch_lmlgrad_dp(int DP, const LmlGradArgs& a, dim3 grid, cudaStream_t s) 
         case 24: lml_grad_kernel<NU, 24><<<grid, 256, 0, s>>>(a); break;
         case 32: lml_grad_kernel<NU, 32><<<grid, 256, 0, s>>>(a); break;
         case 48: lml_grad_kernel<NU, 48><<<grid, 256, 0, s>>>(a); break;
-        default: lml_grad_kernel<NU, 64><<<grid, 256, 0, s>>>(a); break;
+        case 64: lml_grad_kernel<NU, 64><<<grid, 256, 0, s>>>(a); break;
+        case 96: lml_grad_kernel<NU, 96><<<grid, 256, 0, s>>>(a); break;
+        default: lml_grad_kernel<NU, 128><<<grid, 256, 0, s>>>(a); break;
     }
 }
 
@@ -536,7 +548,7 @@ void launch_small_eval(const SmallEvalArgs& a, dim3 grid, size_t smem, cudaStrea
     cudaGetDevice(&dev);
     if (opted_in_device != dev) {
         cudaFuncSetAttribute(small_eval_kernel<NU, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             int(small_eval_smem(SE_MAX_NPAD, DP)));
+                             int(std::min<size_t>(small_eval_smem(SE_MAX_NPAD, DP), 227 * 1024)));
         opted_in_device = dev;
     }
     small_eval_kernel<NU, DP><<<grid, SE_THREADS, smem, s>>>(a);
@@ -550,7 +562,9 @@ void launch_small_eval_dp(int DP, const SmallEvalArgs& a, dim3 grid, size_t smem
         case 24: launch_small_eval<NU, 24>(a, grid, smem, s); break;
         case 32: launch_small_eval<NU, 32>(a, grid, smem, s); break;
         case 48: launch_small_eval<NU, 48>(a, grid, smem, s); break;
-        default: launch_small_eval<NU, 64>(a, grid, smem, s); break;
+        case 64: launch_small_eval<NU, 64>(a, grid, smem, s); break;
+        case 96: launch_small_eval<NU, 96>(a, grid, smem, s); break;
+        default: launch_small_eval<NU, 128>(a, grid, smem, s); break;
     }
 }
 
@@ -558,6 +572,7 @@ void launch_small_eval_dp(int DP, const SmallEvalArgs& a, dim3 grid, size_t smem
 // AOED_SMALL_EVAL=0 sends them down the chunked path instead (tests compare the two).
 bool small_eval_applies(const aoed_gp* gp, int64_t rows, bool want_grad) {
     if (want_grad || gp->Npad > SE_MAX_NPAD || rows > SE_MAX_ROWS) return false;
+    if (small_eval_smem(gp->Npad, gp->DP) > 227 * 1024) return false;  // wide designs on 256 training rows: the chunked kernels
     const char* env = getenv("AOED_SMALL_EVAL");
     return !(env && env[0] == '0');
 }
@@ -676,7 +691,9 @@ void launch_hess_dp(int DP, const HessArgs& a, dim3 grid, cudaStream_t s) {
         case 24: hess_kernel<NU, 24><<<grid, HS_THREADS, 0, s>>>(a); break;
         case 32: hess_kernel<NU, 32><<<grid, HS_THREADS, 0, s>>>(a); break;
         case 48: hess_kernel<NU, 48><<<grid, HS_THREADS, 0, s>>>(a); break;
-        default: hess_kernel<NU, 64><<<grid, HS_THREADS, 0, s>>>(a); break;
+        case 64: hess_kernel<NU, 64><<<grid, HS_THREADS, 0, s>>>(a); break;
+        case 96: hess_kernel<NU, 96><<<grid, HS_THREADS, 0, s>>>(a); break;
+        default: hess_kernel<NU, 128><<<grid, HS_THREADS, 0, s>>>(a); break;
     }
 }
 
@@ -816,7 +833,7 @@ int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu) {
     if (n_var < 1 || n_obj < 1) return fail(AOED_ERR_INVALID, "n_var and n_obj must be positive");
     if (!(nu == 1 || nu == 3 || nu == 5 || nu == -1)) return fail(AOED_ERR_INVALID, "nu must be 1, 3, 5 or -1");
     const int DP = pick_dp(n_var);
-    if (DP < 0) return fail(AOED_ERR_UNSUPPORTED, "n_var > 64 is not supported");
+    if (DP < 0) return fail(AOED_ERR_UNSUPPORTED, "n_var > 128 is not supported");
     DeviceGuard guard_(device);
     CU(guard_.err);
     aoed_gp* gp = new aoed_gp();

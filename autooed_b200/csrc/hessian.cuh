@@ -59,17 +59,18 @@ struct GramArgs {
 };
 
 // one CTA per (candidate, objective); thread per (i, j) pair
-constexpr int GR_MAX_D = 64;
+constexpr int GR_MAX_D = 128;
+constexpr int GR_TT = 32;  // rows of W per shared-memory tile (32 x 129 doubles stay inside 48 KB of static memory)
 constexpr int GR_PPT = GR_MAX_D * GR_MAX_D / HS_THREADS;  // (i, j) pairs per thread at the largest d
 __global__ void __launch_bounds__(HS_THREADS) gram_kernel(GramArgs p) {
-    __shared__ double w[64][GR_MAX_D + 1];
+    __shared__ double w[GR_TT][GR_MAX_D + 1];
     const int c = blockIdx.x, o = blockIdx.y, d = p.d;
     const double* __restrict__ W = p.W + o * p.strideSlab + int64_t(c) * d;
     double acc[GR_PPT];
 #pragma unroll
     for (int u = 0; u < GR_PPT; ++u) acc[u] = 0.0;
-    for (int t0 = 0; t0 < p.N; t0 += 64) {
-        const int nt = min(64, p.N - t0);
+    for (int t0 = 0; t0 < p.N; t0 += GR_TT) {
+        const int nt = min(GR_TT, p.N - t0);
         __syncthreads();
         for (int e = threadIdx.x; e < nt * d; e += HS_THREADS) {
             const int t = e / d, i = e % d;
@@ -186,7 +187,7 @@ __device__ __forceinline__ void acq_second_order(const AcqDev& acq, int o, doubl
 template <int NU, int DP>
 __global__ void __launch_bounds__(HS_THREADS) hess_kernel(HessArgs p) {
     constexpr int PPT = (DP * DP + HS_THREADS - 1) / HS_THREADS;  // (i, j) pairs per thread
-    constexpr int TT = DP > 32 ? HS_TT / 2 : HS_TT;  // the tile of s vectors has to stay inside 48 KB of static memory
+    constexpr int TT = DP > 64 ? HS_TT / 4 : (DP > 32 ? HS_TT / 2 : HS_TT);  // the tile of s vectors has to stay inside 48 KB of static memory
     __shared__ double sS[TT][DP + 1];   // s_t[i] = (x_i - t_i) / l_i^2
     __shared__ double wB[2][TT], wC[2][TT];
     __shared__ double xs[DP], il[DP];

@@ -49,7 +49,7 @@ int nfail(int code, const std::string& msg) { return aoed_detail_fail(code, msg.
         if (rc_ != AOED_OK) return rc_; \
     } while (0)
 
-constexpr int NS_MAX_D = 32;
+constexpr int NS_MAX_D = 64;
 
 struct VarArgs {
     const double* X;      // [n_cur][d] current population (continuous)
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) variation_kernel(VarArgs p) {
     const int pair = gid / p.d, k = gid - pair * p.d;
     if (2 * pair >= p.P) return;
     curandStatePhilox4_32_10_t st;
-    const unsigned long long base = (unsigned long long)(*p.gen) * 4096ull;
+    const unsigned long long base = (unsigned long long)(*p.gen) * 8192ull;  // 64 (k + 1) <= 4160 draws per generation and pair
     curand_init(p.seed, (unsigned long long)pair, base, &st);
     const int ia = tournament(st, p), ib = tournament(st, p);
     const bool do_pair = curand_uniform_double(&st) < p.pc;
@@ -420,7 +420,7 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
                int64_t* h_n_eval) {
     if (!h_X0 || !h_xl || !h_xu || !h_X || !h_F || !h_n_out) return nfail(AOED_ERR_INVALID, "null argument");
     if (n_init < 1 || pop_size < 2 || n_gen < 1) return nfail(AOED_ERR_INVALID, "n_init >= 1, pop_size >= 2, n_gen >= 1 required");
-    if (n_var < 1 || n_var > NS_MAX_D) return nfail(AOED_ERR_UNSUPPORTED, "n_var > 32 is not supported yet");
+    if (n_var < 1 || n_var > NS_MAX_D) return nfail(AOED_ERR_UNSUPPORTED, "n_var > 64 is not supported by the device-resident loop");
     const int d = n_var, m = n_obj, P = pop_size;
     const int64_t cap = std::max<int64_t>(n_init, P);  // the initial sampling is taken as is, even when larger than pop_size
     if (cap + P > RS_MAX_N || rank_small_smem(m, int(cap + P)) > 200 * 1024)

@@ -53,7 +53,7 @@ extern "C" int aoed_rff_eval(int device, int64_t n_rows, int n_var, int n_obj, i
         return rfail(AOED_ERR_INVALID, "bad argument");
     if (n_rows == 0) return AOED_OK;
     if (!h_Xn) return rfail(AOED_ERR_INVALID, "null input");
-    if (n_var > 64) return rfail(AOED_ERR_UNSUPPORTED, "n_var > 64 is not supported");
+    if (n_var > 128) return rfail(AOED_ERR_UNSUPPORTED, "n_var > 128 is not supported");
     const int DP = aoed::rff_dp(n_var);
     const size_t sm = (size_t(n_feat) * DP + 2 * size_t(n_feat)) * sizeof(double);
     if (sm > 200 * 1024) return rfail(AOED_ERR_UNSUPPORTED, "too many spectral points for shared memory");
@@ -108,12 +108,14 @@ extern "C" int aoed_rff_eval(int device, int64_t n_rows, int n_var, int n_obj, i
             RFF_CASE(24)
             RFF_CASE(32)
             RFF_CASE(48)
+            RFF_CASE(64)
+            RFF_CASE(96)
             default:
                 if (sm > 48 * 1024) {
-                    RCU(cudaFuncSetAttribute(rff_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
-                    RCU(cudaFuncSetAttribute(rff_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
+                    RCU(cudaFuncSetAttribute(rff_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
+                    RCU(cudaFuncSetAttribute(rff_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
                 }
-                launch_rff<64>(a, grad, grid, sm, nullptr);
+                launch_rff<128>(a, grad, grid, sm, nullptr);
                 break;
         }
 #undef RFF_CASE

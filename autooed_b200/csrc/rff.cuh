@@ -89,7 +89,9 @@ static __global__ void __launch_bounds__(256) rff_hess_kernel(RffArgs p) {
 }
 
 
-inline int rff_dp(int n_var) { return n_var <= 8 ? 8 : n_var <= 16 ? 16 : n_var <= 24 ? 24 : n_var <= 32 ? 32 : n_var <= 48 ? 48 : 64; }
+inline int rff_dp(int n_var) {
+    return n_var <= 8 ? 8 : n_var <= 16 ? 16 : n_var <= 24 ? 24 : n_var <= 32 ? 32 : n_var <= 48 ? 48 : n_var <= 64 ? 64 : n_var <= 96 ? 96 : 128;
+}
 inline size_t rff_smem_bytes(int n_feat, int DP) { return (size_t(n_feat) * DP + 2 * size_t(n_feat)) * sizeof(double); }
 
 // value-only launch on device buffers (used by the device-resident NSGA-II)
@@ -111,9 +113,17 @@ inline cudaError_t rff_launch_value(const RffArgs& a, cudaStream_t s) {
             if (sm > 48 * 1024) e = cudaFuncSetAttribute(rff_kernel<24, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));
             rff_kernel<24, false><<<grid, 128, sm, s>>>(a);
             break;
-        default:  // the device-resident NSGA-II loop, the only caller, takes n_var <= 32
+        case 32:
             if (sm > 48 * 1024) e = cudaFuncSetAttribute(rff_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));
             rff_kernel<32, false><<<grid, 128, sm, s>>>(a);
+            break;
+        case 48:
+            if (sm > 48 * 1024) e = cudaFuncSetAttribute(rff_kernel<48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));
+            rff_kernel<48, false><<<grid, 128, sm, s>>>(a);
+            break;
+        default:  // the device-resident NSGA-II loop, the only caller, takes n_var <= 64
+            if (sm > 48 * 1024) e = cudaFuncSetAttribute(rff_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));
+            rff_kernel<64, false><<<grid, 128, sm, s>>>(a);
             break;
     }
     return e != cudaSuccess ? e : cudaGetLastError();

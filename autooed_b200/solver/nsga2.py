@@ -246,7 +246,7 @@ class NSGA2(Solver):
         return (self.on_device and getattr(self.real_problem, 'n_constr', 0) == 0
                 and (getattr(acq, 'kind', _lib.ACQ_NONE) != _lib.ACQ_NONE or hasattr(acq, 'device_sample'))
                 and not getattr(acq, 'exact', False)
-                and hasattr(sm, '_ensure_handle') and sm.n_var <= 32 and sm.n_obj <= 8
+                and hasattr(sm, '_ensure_handle') and sm.n_var <= 64 and sm.n_obj <= 8
                 and max(n_init, self.algo.pop_size) + self.algo.pop_size <= 4096)
 
     def _solve(self, X, Y, batch_size):

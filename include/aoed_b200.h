@@ -60,7 +60,7 @@ int aoed_host_free(void* p);
 
 /* ---- model lifecycle ------------------------------------------------------------------------
  * replaces GaussianProcess.__init__ (gp.py:108-135): n_obj independent GPs, kernel selected by nu.
- * 1 <= n_var <= 64 (AOED_ERR_UNSUPPORTED beyond). */
+ * 1 <= n_var <= 128 (AOED_ERR_UNSUPPORTED beyond). */
 int aoed_gp_create(aoed_gp_t** out, int device, int n_var, int n_obj, int nu);
 int aoed_gp_destroy(aoed_gp_t* gp);
 

@@ -12,7 +12,7 @@ def test_cabi_error_codes():
     from autooed_b200 import _lib
     lib = _lib.load()
     h = ctypes.c_void_p()
-    assert lib.aoed_gp_create(ctypes.byref(h), 0, 65, 2, 5) == _lib.ERR_UNSUPPORTED  # n_var > 64
+    assert lib.aoed_gp_create(ctypes.byref(h), 0, 129, 2, 5) == _lib.ERR_UNSUPPORTED  # n_var > 128
     assert b"n_var" in lib.aoed_last_error()
     assert lib.aoed_gp_create(ctypes.byref(h), 0, 4, 2, 7) == _lib.ERR_INVALID       # nu not in {1, 3, 5, -1}
     assert lib.aoed_gp_create(ctypes.byref(h), 99, 4, 2, 5) == _lib.ERR_NO_DEVICE

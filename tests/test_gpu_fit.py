@@ -73,7 +73,7 @@ def test_lml_batch_rank1_kernel_vs_reference():
 
 @pytest.mark.parametrize("nu", [1, 3, 5, -1])
 @pytest.mark.parametrize("shape", [(1, 2, 1), (2, 3, 2), (33, 5, 2), (232, 9, 2), (233, 9, 1), (600, 20, 3), (100, 40, 2),
-                                   (190, 64, 2), (230, 64, 4), (300, 50, 1)])
+                                   (190, 64, 2), (230, 64, 4), (300, 50, 1), (120, 100, 2), (260, 128, 1)])
 def test_lml_batch_vs_oracle(nu, shape):
     """Edge sizes (N = 1, the shared-memory limit 232 / 233, a multi-stream blocked problem) and a non-PD theta."""
     from autooed_b200 import GaussianProcess

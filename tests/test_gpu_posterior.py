@@ -157,7 +157,7 @@ def test_acquisition_fused(name, kind, monkeypatch):
 
 @pytest.mark.parametrize("nu", [1, 3, 5, -1])
 @pytest.mark.parametrize("shape", [(300, 20, 3, 700), (130, 7, 2, 129), (1, 3, 1, 5), (257, 32, 2, 300), (140, 40, 2, 300),
-                                   (300, 64, 2, 150), (90, 33, 1, 40)])
+                                   (300, 64, 2, 150), (90, 33, 1, 40), (150, 70, 2, 60), (140, 100, 1, 50), (100, 128, 2, 30)])
 def test_random_problem_vs_oracle(nu, shape, monkeypatch):
     """Multi-tile / multi-chunk shapes (ragged N, C; chunk of 256 rows forces the double-buffered path)."""
     from autooed_b200 import GaussianProcess
@@ -280,7 +280,7 @@ def test_acquisition_hessian_fused(name, kind, exact):
 
 
 @pytest.mark.parametrize("nu", [1, 3, 5, -1])
-@pytest.mark.parametrize("shape", [(300, 20, 3, 37), (130, 7, 2, 700), (257, 32, 2, 9), (120, 40, 2, 11), (150, 64, 1, 5)])
+@pytest.mark.parametrize("shape", [(300, 20, 3, 37), (130, 7, 2, 700), (257, 32, 2, 9), (120, 40, 2, 11), (150, 64, 1, 5), (90, 100, 1, 3)])
 def test_exact_hessian_vs_oracle_and_fd(nu, shape, monkeypatch):
     """`exact` mode: true second derivatives in raw-Y units; multi-chunk (rows*d > chunk) shapes."""
     from autooed_b200 import GaussianProcess
@@ -370,7 +370,7 @@ def test_variance_closer_to_truth_than_reference(name):
 
 @pytest.mark.parametrize("nu", [1, 3, 5, -1])
 @pytest.mark.parametrize("N,d,rows", [(40, 6, 1), (120, 6, 1000), (129, 20, 37), (256, 32, 530), (7, 3, 4096), (200, 48, 77),
-                                      (256, 64, 300)])
+                                      (256, 64, 300), (100, 100, 64), (256, 128, 40)])
 def test_small_batch_kernel_equals_chunked_path(nu, N, d, rows, monkeypatch):
     """Value-only calls with n_train <= 256 and <= 4096 rows run in one fused kernel (csrc/small_eval.cuh);
     AOED_SMALL_EVAL=0 sends the same call down the chunked xcov / triangular-product / epilogue path.  Same model, same

@@ -75,9 +75,9 @@ def test_large_population_vs_oracle_and_full_fit():
     assert np.isfinite(F).all() and np.isfinite(dF).all()
 
 
-@pytest.mark.parametrize("d", [40, 64])
+@pytest.mark.parametrize("d", [40, 64, 100])
 def test_more_than_32_variables(d):
-    """33 .. 64 design variables: the wider template instances of the fit, posterior and sample kernels, end to end
+    """33 .. 128 design variables: the wider template instances of the fit, posterior and sample kernels, end to end
     (fit on the device, Thompson sample value / gradient / Hessian against the oracle, host NSGA-II on top of it)."""
     from autooed_b200 import GaussianProcess, NSGA2, ThompsonSampling
     from autooed_b200.problem import SimpleProblem
