@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libaoed_b200.so")
-SOURCES = ["gp.cu", "blocked.cu", "fit_launch.cu", "moo.cu", "rff.cu", "nsga2.cu"]
+SOURCES = ["gp.cu", "launch_xcov.cu", "launch_fitk.cu", "launch_small_eval.cu", "launch_hess.cu", "blocked.cu", "fit_launch.cu",
+           "fit_launch_nu1.cu", "fit_launch_nu3.cu", "fit_launch_nu5.cu", "fit_launch_rbf.cu", "moo.cu", "rff.cu", "nsga2.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "aoed_b200.h")]
 
 
@@ -37,7 +38,7 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "6"]  # the sources compile concurrently
+           "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "0"]  # the sources compile concurrently
     for macro in ("AOED_XCOV_UNROLL", "AOED_XCOV_MINBLOCKS", "AOED_XCOV_XS_SMEM"):  # tuning experiments; defaults live in posterior.cuh
         if os.environ.get(macro):
             cmd += [f"-D{macro}={os.environ[macro]}"]

@@ -12,6 +12,7 @@
 
 #include "../../include/aoed_b200.h"
 #include "blocked.h"
+#include "launchers.h"
 #include "fit.cuh"
 #include "fit_small.cuh"
 #include "fit_small2.cuh"
@@ -239,142 +240,6 @@ void choose_split(int N, int colTiles, int m, int js_cap, int ctas_per_wave, int
     jchunk = round_up((N + JS - 1) / JS, XC_JT);
 }
 
-// effective width of the thread-per-candidate kernels: DP - 4 when the design fits (see xcov_kernel)
-int pick_de(int d, int DP) { return (DP <= 32 && d <= DP - 4) ? DP - 4 : DP; }
-
-template <int NU, int DP, int DE>
-void launch_xcov(const XcovArgs& a, dim3 grid, bool grad, cudaStream_t s) {
-    if (grad)
-        xcov_kernel<NU, DP, true, DE><<<grid, XC_THREADS, 0, s>>>(a);
-    else
-        xcov_kernel<NU, DP, false, DE><<<grid, XC_THREADS, 0, s>>>(a);
-}
-
-template <int DP, int DE>
-void launch_xcov_nu(int nu, const XcovArgs& a, dim3 grid, bool grad, cudaStream_t s) {
-    switch (nu) {
-        case 1: launch_xcov<1, DP, DE>(a, grid, grad, s); break;
-        case 3: launch_xcov<3, DP, DE>(a, grid, grad, s); break;
-        case 5: launch_xcov<5, DP, DE>(a, grid, grad, s); break;
-        default: launch_xcov<-1, DP, DE>(a, grid, grad, s); break;
-    }
-}
-
-void launch_xcov_any(int nu, int DP, int DE, const XcovArgs& a, dim3 grid, bool grad, cudaStream_t s) {
-    switch (DP * 100 + DE) {
-        case 804: launch_xcov_nu<8, 4>(nu, a, grid, grad, s); break;
-        case 808: launch_xcov_nu<8, 8>(nu, a, grid, grad, s); break;
-        case 1612: launch_xcov_nu<16, 12>(nu, a, grid, grad, s); break;
-        case 1616: launch_xcov_nu<16, 16>(nu, a, grid, grad, s); break;
-        case 2420: launch_xcov_nu<24, 20>(nu, a, grid, grad, s); break;
-        case 2424: launch_xcov_nu<24, 24>(nu, a, grid, grad, s); break;
-        case 3228: launch_xcov_nu<32, 28>(nu, a, grid, grad, s); break;
-        case 3232: launch_xcov_nu<32, 32>(nu, a, grid, grad, s); break;
-        case 4848: launch_xcov_nu<48, 48>(nu, a, grid, grad, s); break;
-        case 6464: launch_xcov_nu<64, 64>(nu, a, grid, grad, s); break;
-        case 9696: launch_xcov_nu<96, 96>(nu, a, grid, grad, s); break;
-        default: launch_xcov_nu<128, 128>(nu, a, grid, grad, s); break;
-    }
-}
-
-template <typename K>
-int occ_of(K kernel, int threads) {
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 1;
-    return n;
-}
-
-template <int DP, int DE>
-void occ_pair(int nu, int& occ_xcov, int& occ_gradsum) {
-    switch (nu) {
-        case 1: occ_xcov = occ_of(xcov_kernel<1, DP, true, DE>, XC_THREADS); break;
-        case 3: occ_xcov = occ_of(xcov_kernel<3, DP, true, DE>, XC_THREADS); break;
-        case 5: occ_xcov = occ_of(xcov_kernel<5, DP, true, DE>, XC_THREADS); break;
-        default: occ_xcov = occ_of(xcov_kernel<-1, DP, true, DE>, XC_THREADS); break;
-    }
-    occ_gradsum = occ_of(gradsum_kernel<DP, DE>, XC_THREADS);
-}
-
-void query_occupancy(int nu, int DP, int DE, int& occ_xcov, int& occ_gradsum) {
-    switch (DP * 100 + DE) {
-        case 804: occ_pair<8, 4>(nu, occ_xcov, occ_gradsum); break;
-        case 808: occ_pair<8, 8>(nu, occ_xcov, occ_gradsum); break;
-        case 1612: occ_pair<16, 12>(nu, occ_xcov, occ_gradsum); break;
-        case 1616: occ_pair<16, 16>(nu, occ_xcov, occ_gradsum); break;
-        case 2420: occ_pair<24, 20>(nu, occ_xcov, occ_gradsum); break;
-        case 2424: occ_pair<24, 24>(nu, occ_xcov, occ_gradsum); break;
-        case 3228: occ_pair<32, 28>(nu, occ_xcov, occ_gradsum); break;
-        case 3232: occ_pair<32, 32>(nu, occ_xcov, occ_gradsum); break;
-        case 4848: occ_pair<48, 48>(nu, occ_xcov, occ_gradsum); break;
-        case 6464: occ_pair<64, 64>(nu, occ_xcov, occ_gradsum); break;
-        case 9696: occ_pair<96, 96>(nu, occ_xcov, occ_gradsum); break;
-        default: occ_pair<128, 128>(nu, occ_xcov, occ_gradsum); break;
-    }
-}
-
-void launch_gradsum(int DP, int DE, const GradsumArgs& a, dim3 grid, cudaStream_t s) {
-    switch (DP * 100 + DE) {
-        case 804: gradsum_kernel<8, 4><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 808: gradsum_kernel<8, 8><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 1612: gradsum_kernel<16, 12><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 1616: gradsum_kernel<16, 16><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 2420: gradsum_kernel<24, 20><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 2424: gradsum_kernel<24, 24><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 3228: gradsum_kernel<32, 28><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 3232: gradsum_kernel<32, 32><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 4848: gradsum_kernel<48, 48><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 6464: gradsum_kernel<64, 64><<<grid, XC_THREADS, 0, s>>>(a); break;
-        case 9696: gradsum_kernel<96, 96><<<grid, XC_THREADS, 0, s>>>(a); break;
-        default: gradsum_kernel<128, 128><<<grid, XC_THREADS, 0, s>>>(a); break;
-    }
-}
-
-template <int NU>
-void launch_kmat_dp(int DP, const KmatArgs& a, dim3 grid, cudaStream_t s) {
-    switch (DP) {
-        case 8: kmat_kernel<NU, 8><<<grid, 256, 0, s>>>(a); break;
-        case 16: kmat_kernel<NU, 16><<<grid, 256, 0, s>>>(a); break;
-        case 24: kmat_kernel<NU, 24><<<grid, 256, 0, s>>>(a); break;
-        case 32: kmat_kernel<NU, 32><<<grid, 256, 0, s>>>(a); break;
-        case 48: kmat_kernel<NU, 48><<<grid, 256, 0, s>>>(a); break;
-        case 64: kmat_kernel<NU, 64><<<grid, 256, 0, s>>>(a); break;
-        case 96: kmat_kernel<NU, 96><<<grid, 256, 0, s>>>(a); break;
-        default: kmat_kernel<NU, 128><<<grid, 256, 0, s>>>(a); break;
-    }
-}
-
-void launch_kmat(int nu, int DP, const KmatArgs& a, dim3 grid, cudaStream_t s) {
-    switch (nu) {
-        case 1: launch_kmat_dp<1>(DP, a, grid, s); break;
-        case 3: launch_kmat_dp<3>(DP, a, grid, s); break;
-        case 5: launch_kmat_dp<5>(DP, a, grid, s); break;
-        default: launch_kmat_dp<-1>(DP, a, grid, s); break;
-    }
-}
-
-template <int NU>
-void launch_lmlgrad_dp(int DP, const LmlGradArgs& a, dim3 grid, cudaStream_t s) {
-    switch (DP) {
-        case 8: lml_grad_kernel<NU, 8><<<grid, 256, 0, s>>>(a); break;
-        case 16: lml_grad_kernel<NU, 16><<<grid, 256, 0, s>>>(a); break;
-        case 24: lml_grad_kernel<NU, 24><<<grid, 256, 0, s>>>(a); break;
-        case 32: lml_grad_kernel<NU, 32><<<grid, 256, 0, s>>>(a); break;
-        case 48: lml_grad_kernel<NU, 48><<<grid, 256, 0, s>>>(a); break;
-        case 64: lml_grad_kernel<NU, 64><<<grid, 256, 0, s>>>(a); break;
-        case 96: lml_grad_kernel<NU, 96><<<grid, 256, 0, s>>>(a); break;
-        default: lml_grad_kernel<NU, 128><<<grid, 256, 0, s>>>(a); break;
-    }
-}
-
-void launch_lmlgrad(int nu, int DP, const LmlGradArgs& a, dim3 grid, cudaStream_t s) {
-    switch (nu) {
-        case 1: launch_lmlgrad_dp<1>(DP, a, grid, s); break;
-        case 3: launch_lmlgrad_dp<3>(DP, a, grid, s); break;
-        case 5: launch_lmlgrad_dp<5>(DP, a, grid, s); break;
-        default: launch_lmlgrad_dp<-1>(DP, a, grid, s); break;
-    }
-}
-
 template <bool UPPER, int TNV>
 int launch_trmm_cfg(const TrmmArgs& a, int colTiles128, int batch, cudaStream_t s) {
     static bool attr_set[64] = {false};  // function attributes are per device
@@ -541,33 +406,6 @@ struct EvalOut {
     double *F, *S, *dF, *dS, *A, *dA;
 };
 
-template <int NU, int DP>
-void launch_small_eval(const SmallEvalArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
-    static thread_local int opted_in_device = -1;  // shared-memory opt-in (up to 105 KB at n_train 256, d 32): once per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (opted_in_device != dev) {
-        cudaFuncSetAttribute(small_eval_kernel<NU, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             int(std::min<size_t>(small_eval_smem(SE_MAX_NPAD, DP), 227 * 1024)));
-        opted_in_device = dev;
-    }
-    small_eval_kernel<NU, DP><<<grid, SE_THREADS, smem, s>>>(a);
-}
-
-template <int NU>
-void launch_small_eval_dp(int DP, const SmallEvalArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
-    switch (DP) {
-        case 8: launch_small_eval<NU, 8>(a, grid, smem, s); break;
-        case 16: launch_small_eval<NU, 16>(a, grid, smem, s); break;
-        case 24: launch_small_eval<NU, 24>(a, grid, smem, s); break;
-        case 32: launch_small_eval<NU, 32>(a, grid, smem, s); break;
-        case 48: launch_small_eval<NU, 48>(a, grid, smem, s); break;
-        case 64: launch_small_eval<NU, 64>(a, grid, smem, s); break;
-        case 96: launch_small_eval<NU, 96>(a, grid, smem, s); break;
-        default: launch_small_eval<NU, 128>(a, grid, smem, s); break;
-    }
-}
-
 // value-only calls on small batches and small training sets: one fused kernel (small_eval.cuh).
 // AOED_SMALL_EVAL=0 sends them down the chunked path instead (tests compare the two).
 bool small_eval_applies(const aoed_gp* gp, int64_t rows, bool want_grad) {
@@ -584,12 +422,7 @@ int eval_small(aoed_gp* gp, const double* d_X, int64_t rows, bool want_std, cons
     a.F = out.F; a.S = out.S; a.A = out.A;
     const dim3 grid(unsigned((rows + SE_TC - 1) / SE_TC), gp->m);
     const size_t smem = small_eval_smem(gp->Npad, gp->DP);
-    switch (gp->nu) {
-        case 1: launch_small_eval_dp<1>(gp->DP, a, grid, smem, s); break;
-        case 3: launch_small_eval_dp<3>(gp->DP, a, grid, smem, s); break;
-        case 5: launch_small_eval_dp<5>(gp->DP, a, grid, smem, s); break;
-        default: launch_small_eval_dp<-1>(gp->DP, a, grid, smem, s); break;
-    }
+    launch_small_eval_any(gp->nu, gp->DP, a, grid, smem, s);
     gp->n_launches++;
     CU(cudaGetLastError());
     return AOED_OK;
@@ -681,29 +514,6 @@ int make_acq(const aoed_gp* gp, int kind, uint32_t flags, const double* param, A
         for (int o = 0; o < gp->m; ++o) acq.y_min[o] = param[o];
     }
     return AOED_OK;
-}
-
-template <int NU>
-void launch_hess_dp(int DP, const HessArgs& a, dim3 grid, cudaStream_t s) {
-    switch (DP) {
-        case 8: hess_kernel<NU, 8><<<grid, HS_THREADS, 0, s>>>(a); break;
-        case 16: hess_kernel<NU, 16><<<grid, HS_THREADS, 0, s>>>(a); break;
-        case 24: hess_kernel<NU, 24><<<grid, HS_THREADS, 0, s>>>(a); break;
-        case 32: hess_kernel<NU, 32><<<grid, HS_THREADS, 0, s>>>(a); break;
-        case 48: hess_kernel<NU, 48><<<grid, HS_THREADS, 0, s>>>(a); break;
-        case 64: hess_kernel<NU, 64><<<grid, HS_THREADS, 0, s>>>(a); break;
-        case 96: hess_kernel<NU, 96><<<grid, HS_THREADS, 0, s>>>(a); break;
-        default: hess_kernel<NU, 128><<<grid, HS_THREADS, 0, s>>>(a); break;
-    }
-}
-
-void launch_hess(int nu, int DP, const HessArgs& a, dim3 grid, cudaStream_t s) {
-    switch (nu) {
-        case 1: launch_hess_dp<1>(DP, a, grid, s); break;
-        case 3: launch_hess_dp<3>(DP, a, grid, s); break;
-        case 5: launch_hess_dp<5>(DP, a, grid, s); break;
-        default: launch_hess_dp<-1>(DP, a, grid, s); break;
-    }
 }
 
 // rows of candidates per chunk on the Hessian path: the d k*/dx_i right-hand sides take rows*d slab columns

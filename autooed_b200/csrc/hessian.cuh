@@ -32,7 +32,7 @@ struct DkcolArgs {
     int rows, d, DP, N, Npad, ldc, ldx, JS, jchunk;
 };
 
-__global__ void __launch_bounds__(128) dkcol_kernel(DkcolArgs p) {
+static __global__ void __launch_bounds__(128) dkcol_kernel(DkcolArgs p) {
     const int col = blockIdx.x * 128 + threadIdx.x;
     const int js = blockIdx.y, o = blockIdx.z;
     const int ncol = p.rows * p.d;
@@ -62,7 +62,7 @@ struct GramArgs {
 constexpr int GR_MAX_D = 128;
 constexpr int GR_TT = 32;  // rows of W per shared-memory tile (32 x 129 doubles stay inside 48 KB of static memory)
 constexpr int GR_PPT = GR_MAX_D * GR_MAX_D / HS_THREADS;  // (i, j) pairs per thread at the largest d
-__global__ void __launch_bounds__(HS_THREADS) gram_kernel(GramArgs p) {
+static __global__ void __launch_bounds__(HS_THREADS) gram_kernel(GramArgs p) {
     __shared__ double w[GR_TT][GR_MAX_D + 1];
     const int c = blockIdx.x, o = blockIdx.y, d = p.d;
     const double* __restrict__ W = p.W + o * p.strideSlab + int64_t(c) * d;

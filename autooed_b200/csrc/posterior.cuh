@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(XC_THREADS) gradsum_kernel(GradsumArgs p) {
 }
 
 // Transposes the candidate chunk [rows][d] (row-major, as numpy hands it over) to [DP][ldc].
-__global__ void transpose_x_kernel(const double* __restrict__ X, int64_t rows, int d, int DP, int ldc,
+static __global__ void transpose_x_kernel(const double* __restrict__ X, int64_t rows, int d, int DP, int ldc,
                                    double* __restrict__ XT) {
     const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (c >= ldc) return;
@@ -306,7 +306,7 @@ constexpr int EPI_CX = 32;  // candidates per CTA
 constexpr int EPI_KY = 8;   // threads per candidate: the partial-sum reads (~470 per candidate and objective) are split
                             // over them, otherwise the few thousand candidates of a chunk leave the GPU latency bound
 
-__global__ void __launch_bounds__(EPI_CX * EPI_KY) epilogue_kernel(EpilogueArgs p) {
+static __global__ void __launch_bounds__(EPI_CX * EPI_KY) epilogue_kernel(EpilogueArgs p) {
     __shared__ double sc[4][EPI_CX];  // mu, sum of squares, s0, t0 per candidate
     const int cx = threadIdx.x, ky = threadIdx.y;
     const int64_t c = blockIdx.x * int64_t(EPI_CX) + cx;
