@@ -45,14 +45,15 @@ def build(force=False, verbose=False):
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ["-o", LIB]
+    out = os.environ.get("AOED_BUILD_OUT", LIB)  # tuning variants are built next to the library and selected with AOED_LIB
+    cmd += ["-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libaoed_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

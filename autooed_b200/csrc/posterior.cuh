@@ -196,6 +196,8 @@ struct GradsumArgs {
     int N, Npad, ldc, JS, jchunk;
 };
 
+constexpr int GS_B = 8;  // training points per register batch
+
 template <int DP, int DE = DP>
 __global__ void __launch_bounds__(XC_THREADS) gradsum_kernel(GradsumArgs p) {
     __shared__ __align__(16) double ts[XC_JT][DP];
@@ -210,30 +212,41 @@ __global__ void __launch_bounds__(XC_THREADS) gradsum_kernel(GradsumArgs p) {
     for (int k = 0; k < DE; ++k) sk[k] = 0.0;
     const int j_begin = js * p.jchunk;
     const int j_end = min(p.N, j_begin + p.jchunk);
+    // The kernel is HBM bound (two 8-byte streams per training point against 1 + DE FMAs): the loads of the NEXT eight
+    // points are issued before the current eight are used, so a warp always has a batch in flight while it computes.
+    auto fetch = [&](int jb, double (&buf)[GS_B]) {
+#pragma unroll
+        for (int u = 0; u < GS_B; ++u) {
+            const int j = min(jb + u, j_end - 1);
+            const double v = Gr[int64_t(j) * p.ldc] * V[int64_t(j) * p.ldc];
+            buf[u] = (jb + u < j_end) ? v : 0.0;
+        }
+    };
+    double cur[GS_B], nxt[GS_B];
+    if (j_begin < j_end) fetch(j_begin, cur);
     for (int j0 = j_begin; j0 < j_end; j0 += XC_JT) {
         const int nj = min(XC_JT, j_end - j0);
         __syncthreads();
         for (int i = tid; i < nj * DP; i += XC_THREADS) (&ts[0][0])[i] = Ts[int64_t(j0) * DP + i];
         __syncthreads();
-        // the kernel is HBM bound (two 8-byte streams per training point): issue the loads of 8 points before using them
-        for (int jb = 0; jb < nj; jb += 8) {
-            double wv[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int jj = min(jb + u, nj - 1);
-                const double pr = Gr[int64_t(j0 + jj) * p.ldc] * V[int64_t(j0 + jj) * p.ldc];
-                wv[u] = (jb + u < nj) ? pr : 0.0;
-            }
+        for (int b = 0; b < XC_JT / GS_B; ++b) {
+            const int jb = b * GS_B;
+            if (jb < nj) {
+                if (j0 + jb + GS_B < j_end) fetch(j0 + jb + GS_B, nxt);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int jj = min(jb + u, nj - 1);
-                s0 += wv[u];
+                for (int u = 0; u < GS_B; ++u) {
+                    const int jj = min(jb + u, nj - 1);  // past the end: cur[u] == 0
+                    s0 += cur[u];
 #pragma unroll
-                for (int k = 0; k < DE; k += 2) {
-                    double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
-                    sk[k] = fma(wv[u], t.x, sk[k]);
-                    sk[k + 1] = fma(wv[u], t.y, sk[k + 1]);
+                    for (int k = 0; k < DE; k += 2) {
+                        double2 t = *reinterpret_cast<const double2*>(&ts[jj][k]);
+                        sk[k] = fma(cur[u], t.x, sk[k]);
+                        sk[k + 1] = fma(cur[u], t.y, sk[k + 1]);
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < GS_B; ++u) cur[u] = nxt[u];
             }
         }
     }
