@@ -55,6 +55,8 @@ SIGNATURES = {
     "aoed_hvi_select": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, _vp, ctypes.c_int64, _vp, _vp,
                                        ctypes.c_int, _vp, _vp, _vp]),
     "aoed_hv_contributions": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, _vp, ctypes.c_int64, _vp, _vp, _vp]),
+    "aoed_graph_cut": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp,
+                                      ctypes.POINTER(ctypes.c_int64)]),
 }
 
 _lib = None

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libaoed_b200.so")
 SOURCES = ["gp.cu", "launch_xcov.cu", "launch_fitk.cu", "launch_small_eval.cu", "launch_hess.cu", "blocked.cu", "fit_launch.cu",
-           "fit_launch_nu1.cu", "fit_launch_nu3.cu", "fit_launch_nu5.cu", "fit_launch_rbf.cu", "moo.cu", "rff.cu", "nsga2.cu"]
+           "fit_launch_nu1.cu", "fit_launch_nu3.cu", "fit_launch_nu5.cu", "fit_launch_rbf.cu", "moo.cu", "rff.cu", "nsga2.cu", "graphcut.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "aoed_b200.h")]
 
 

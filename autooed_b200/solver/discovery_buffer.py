@@ -6,13 +6,33 @@ sorted by distance, an insert classifies the whole batch at once (cell index, di
 with the reference's own `np.argsort` of [old content ..., new rows in insertion order], so the kept samples and their
 order — including ties — are the reference's.  `sample` consumes the global numpy RNG exactly as the reference does.
 
-`sparse_approximation` (:203-284) is an alpha-expansion graph cut through `pygco`, which is not installable here.  The
-fallback implemented below minimises the UNARY term of the same energy only (no smoothness, no label cost): every
-non-empty cell is labelled with the patch of its best sample, i.e. the cut's solution for label_cost = pairwise weight =
-0.  It returns the same triple (labels, approx_x, approx_y) with the same remapping of patch ids; when `pygco` is
-importable the reference's graph cut runs instead.
+`sparse_approximation` (:203-284) labels the non-empty cells by an alpha-expansion graph cut.  The reference calls the
+third-party `pygco.cut_from_graph(edges, unary, pairwise, label_cost)` (its fourth positional parameter is `n_iter`, so
+`label_cost` acts as the cycle limit); pygco is neither in the reference tree nor installable here, so the cut is the
+library's own host routine `aoed_graph_cut` (csrc/graphcut.cu: the same energy, the same int32 costs, expansion moves
+solved exactly by max-flow, labels starting at 0, alpha in ascending order).  Where gco's tie handling differs the two can
+return different labelings of equal energy class — parity against pygco itself is unpinned; when `pygco` is importable
+it is used, as in the reference.
 """
 import numpy as np
+
+
+def graph_cut(edges, unary, pairwise, n_iter=-1, return_energy=False):
+    """`pygco.cut_from_graph(edges, unary_cost, pairwise_cost, n_iter)` on the library's own alpha-expansion
+    (include/aoed_b200.h `aoed_graph_cut`): int32 inputs, labels (n_node,) int32 out."""
+    import ctypes
+
+    from .. import _lib
+    edges = np.ascontiguousarray(np.asarray(edges, dtype=np.int32).reshape(-1, 2))
+    unary = np.ascontiguousarray(unary, dtype=np.int32)
+    pairwise = np.ascontiguousarray(pairwise, dtype=np.int32)
+    n_node, n_label = unary.shape
+    assert pairwise.shape == (n_label, n_label)
+    labels = np.zeros(n_node, dtype=np.int32)
+    energy = ctypes.c_int64(0)
+    _lib.check(_lib.load().aoed_graph_cut(n_node, len(edges), _lib.ptr(edges), n_label, _lib.ptr(unary), _lib.ptr(pairwise),
+                                          int(n_iter), _lib.ptr(labels), ctypes.byref(energy)))
+    return (labels, energy.value) if return_energy else labels
 
 
 def generate_weights_batch(n_dim, delta_weight):
@@ -158,28 +178,28 @@ class BufferBase:
 
     # -- sparse approximation ----------------------------------------------------------------------------------------
     def sparse_approximation(self):
-        """buffer.py:203-284 (see the module docstring for the pygco-free fallback)."""
+        """buffer.py:203-284 (see the module docstring for the graph cut)."""
         mapping = {}
         for c in self.cells:  # remap patch ids to 0 .. n_label-1 in order of first appearance (:217-226)
             for i, p in enumerate(c.pid):
                 c.pid[i] = mapping.setdefault(int(p), len(mapping))
         valid_cells = np.array([i for i, c in enumerate(self.cells) if len(c) > 0])
         n_label = len(mapping)
-        try:
-            from pygco import cut_from_graph
-        except ImportError:
-            cut_from_graph = None
-        if cut_from_graph is not None and len(valid_cells) > 1:
+        if len(valid_cells) > 1:
             unary = self.C_inf * np.ones((len(valid_cells), n_label))
             pairwise = -self.C_inf * np.eye(n_label)
             for i, idx in enumerate(valid_cells):
                 c = self.cells[idx]
                 unary[i, c.pid] = np.minimum((c.dist - c.dist.min()) / self.delta_b, self.C_inf)
             edges = self._get_graph_edges(valid_cells)
-            labels_opt = cut_from_graph(edges.astype(np.int32), unary.astype(np.int32), pairwise.astype(np.int32),
-                                        np.int32(self.label_cost))
+            edges, unary, pairwise = edges.astype(np.int32), unary.astype(np.int32), pairwise.astype(np.int32)
+            try:
+                from pygco import cut_from_graph
+                labels_opt = cut_from_graph(edges, unary, pairwise, np.int32(self.label_cost))
+            except ImportError:
+                labels_opt = graph_cut(edges, unary, pairwise, int(self.label_cost))
         else:
-            labels_opt = [int(self.cells[idx].pid[0]) for idx in valid_cells]  # unary-only minimiser: the best sample's patch
+            labels_opt = [int(self.cells[idx].pid[0]) for idx in valid_cells]  # one node: the unary minimiser
         approx_x, approx_y, labels = [], [], []
         for idx, label in zip(valid_cells, labels_opt):
             c = self.cells[idx]

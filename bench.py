@@ -869,7 +869,7 @@ def run_discovery_mode(args):
                       "s_total": dt, "s_per_generation": dt / 10, "surrogate_rows_evaluated": int(solver.n_eval),
                       "buffer_samples": int(algo.buffer.sample_count), "families": int(len(set(int(l) for l in algo.fam_lbls))),
                       "approx_front_size": int(len(algo.approx_front)), "proposed": [int(Xc.shape[0]), int(Xc.shape[1])],
-                      "sparse_approximation": "unary-only fallback (pygco absent)"}), flush=True)
+                      "sparse_approximation": "aoed_graph_cut (own alpha-expansion; pygco absent)"}), flush=True)
 
     xs = rng.random((pop, d))
     bounds = np.stack([np.zeros(d), np.ones(d)])

@@ -48,21 +48,28 @@ def test_buffer_insert_move_origin_sample_equal_reference(tag):
     assert [len(c) for c in buf.buffer_x] == list(Z[f"{tag}_after{int(Z[tag + '_n_ins']) - 1}_sizes"])
 
 
-def test_sparse_approximation_fallback_labels_the_best_patch_of_every_cell():
-    """Without pygco the unary-only minimiser of the same energy: one representative per non-empty cell, labelled with the
-    patch of the cell's closest sample, patch ids remapped in order of first appearance (buffer.py:217-226)."""
-    buf = db.Buffer2D(8, cell_size=3)
-    rng = np.random.default_rng(0)
-    X, Y = rng.random((40, 3)), rng.random((40, 2)) + 0.1
-    pid = rng.integers(20, 25, 40)
-    buf.insert(X, Y, pid)
-    labels, ax, ay = buf.sparse_approximation()
-    valid = [c for c in buf.cells if len(c)]
-    assert len(labels) == len(valid) == len(ax) == len(ay)
-    seen = np.concatenate([c.pid for c in valid])
-    assert set(seen) == set(range(len(set(seen))))  # remapped to 0 .. n_label-1
-    for lab, x, y, c in zip(labels, ax, ay, valid):
-        assert lab == c.pid[0] and np.array_equal(x, c.x[0]) and np.array_equal(y, c.y[0])
+def test_sparse_approximation_structure_and_cycle_limit():
+    """One representative per non-empty cell, patch ids remapped in order of first appearance (buffer.py:217-226); the
+    representative is the closest sample of the chosen patch, or the cell's closest sample when the cell has none of that
+    patch (:263-274).  `label_cost` reaches the cut as its cycle limit (the reference passes it as pygco's fourth positional
+    argument, `n_iter`): the default 0 allows no move, every cell keeps label 0.  The cut itself: tests/test_graph_cut.py."""
+    for label_cost in (0, 10):
+        buf = db.Buffer2D(8, cell_size=3, label_cost=label_cost)
+        rng = np.random.default_rng(0)
+        X, Y = rng.random((40, 3)), rng.random((40, 2)) + 0.1
+        pid = rng.integers(20, 25, 40)
+        buf.insert(X, Y, pid)
+        labels, ax, ay = buf.sparse_approximation()
+        valid = [c for c in buf.cells if len(c)]
+        assert len(labels) == len(valid) == len(ax) == len(ay)
+        seen = np.concatenate([c.pid for c in valid])
+        assert set(seen) == set(range(len(set(seen))))  # remapped to 0 .. n_label-1
+        if label_cost == 0:
+            assert not np.any(labels)
+        for lab, x, y, c in zip(labels, ax, ay, valid):
+            hit = np.flatnonzero(c.pid == lab)
+            j = hit[0] if len(hit) else 0
+            assert np.array_equal(x, c.x[j]) and np.array_equal(y, c.y[j])
 
 
 @pytest.mark.parametrize("tag", ["ss_free", "ss_constr"])
