@@ -58,6 +58,7 @@ struct VarArgs {
     int m;
     const double *xl, *xu;
     double* Xoff;         // [P][d] offspring (continuous)
+    double* Xn;           // [P][d] the same, normalised to the unit box as the surrogate wants them
     int n_cur, P, d;
     unsigned long long seed;
     const int* gen;       // generation number, on the device so that a captured graph of the loop can be replayed
@@ -128,8 +129,14 @@ __global__ void __launch_bounds__(128) variation_kernel(VarArgs p) {
     const double m2 = curand_uniform_double(&st), v2 = curand_uniform_double(&st);
     if (m1 < pm) x1 = poly_mutate(x1, lo, hi, v1, p.eta_m);
     if (m2 < pm) x2 = poly_mutate(x2, lo, hi, v2, p.eta_m);
+    // also in normalised form, Xn = clip((X - xl) / (xu - xl), 0, 1) (utils/normalization.py:31-32; the expression of
+    // normalize_kernel below), so that the evaluator starts right after this kernel
     p.Xoff[int64_t(2 * pair) * p.d + k] = x1;
-    if (2 * pair + 1 < p.P) p.Xoff[int64_t(2 * pair + 1) * p.d + k] = x2;
+    p.Xn[int64_t(2 * pair) * p.d + k] = fmin(fmax((x1 - lo) / (hi - lo), 0.0), 1.0);
+    if (2 * pair + 1 < p.P) {
+        p.Xoff[int64_t(2 * pair + 1) * p.d + k] = x2;
+        p.Xn[int64_t(2 * pair + 1) * p.d + k] = fmin(fmax((x2 - lo) / (hi - lo), 0.0), 1.0);
+    }
 }
 
 // Xn = clip((X - xl) / (xu - xl), 0, 1): the normalisation SurrogateModel.evaluate applies (utils/normalization.py:31-32)
@@ -508,18 +515,43 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
     const auto t_loop = std::chrono::steady_clock::now();
     const int one = 1;
     NCU(cudaMemcpyAsync(bGen.p, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    // The duplicate scan needs only the offspring coordinates, the evaluator only their normalised copy: the two run side by
+    // side (second stream; in the captured graph two branches that join at the merge), which takes the scan — 6 us at
+    // P = 200, 20 us at P = 1000 — off the critical path of a generation.
+    cudaStream_t s2 = nullptr;
+    NCU(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    StreamGuard sguard2{s2};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    NCU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    NCU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    struct EventGuard {
+        cudaEvent_t a, b;
+        ~EventGuard() {
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    } eguard{ev_fork, ev_join};
+    const char* fork_env = getenv("AOED_NSGA2_FORK");  // =0: one serial stream (the per-phase stamps want that too)
+    const bool serial = stamp || (fork_env && fork_env[0] == '0');
     auto generation = [&]() -> int {
         VarArgs va;
         va.X = bX[cur].as<double>(); va.F = bF[cur].as<double>(); va.m = m; va.crowd = bC[cur].as<double>();
-        va.xl = bXl.as<double>(); va.xu = bXu.as<double>(); va.Xoff = bXoff.as<double>();
+        va.xl = bXl.as<double>(); va.xu = bXu.as<double>(); va.Xoff = bXoff.as<double>(); va.Xn = bXn.as<double>();
         va.n_cur = n_cur; va.P = P; va.d = d; va.seed = seed; va.gen = bGen.as<int>(); va.pc = 0.9; va.eta_c = 15.0; va.eta_m = 20.0;
         mark(0);
         variation_kernel<<<((P + 1) / 2 * d + 127) / 128, 128, 0, s>>>(va);
         mark(1);
-        duplicate_kernel<<<(P + DUP_WARPS - 1) / DUP_WARPS, 32 * DUP_WARPS, size_t(n_cur + P) * sizeof(double), s>>>(
+        cudaStream_t sdup = serial ? s : s2;
+        if (!serial) {
+            NCU(cudaEventRecord(ev_fork, s));
+            NCU(cudaStreamWaitEvent(s2, ev_fork, 0));
+        }
+        duplicate_kernel<<<(P + DUP_WARPS - 1) / DUP_WARPS, 32 * DUP_WARPS, size_t(n_cur + P) * sizeof(double), sdup>>>(
             bX[cur].as<double>(), n_cur, bXoff.as<double>(), P, d, bDup.as<uint8_t>(), bEval.as<unsigned long long>(), bGen.as<int>());
+        if (!serial) NCU(cudaEventRecord(ev_join, s2));
         mark(2);
-        NCHK(evaluate(bXoff.as<double>(), P, bFoff.as<double>()));
+        NCHK(eval_fn(s, bXn.as<double>(), P, bFoff.as<double>()));
+        if (!serial) NCU(cudaStreamWaitEvent(s, ev_join, 0));
         mark(3);
         NCHK(survive(cur, n_cur, bXoff.as<double>(), bFoff.as<double>(), bDup.as<uint8_t>(), P, P, cur ^ 1));
         cur ^= 1;
