@@ -128,6 +128,62 @@ def _cpu_port_rate(n_train, d, m, nu, budget_s, chunk=1024):
     return done / el, done, el
 
 
+def reference_literal(w, n_train=None, rows=512, loop_rows=24):
+    """SURVEY.md §8(d) baselines B1 / B3, informational: the UNMODIFIED reference classes (`autooed/mobo/surrogate_model/gp.py`,
+    `acquisition/ucb.py`, staged under the git-ignored baseline/_ref/ by `__graft_entry__.build()` where the reference tree is
+    mounted) with sklearn's own `GaussianProcessRegressor` underneath, on the workload's training set and fixed theta
+    (`optimizer=None`, so `fit` is one factorisation).  The reference can only produce d sigma / dx for ONE row per call
+    (SURVEY B-1), so "std + gradient" is a row loop; the batched calls are its `std=True` (no gradient) and its
+    `std=False, gradient=True` forms.  Not the `value` of the reference arm — that stays the vectorised port, the stronger
+    comparator."""
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref")
+    if not os.path.isfile(os.path.join(root, "autooed", "mobo", "surrogate_model", "gp.py")):
+        return {"unavailable": "baseline/_ref holds no staged reference modules (run __graft_entry__.build() where /root/reference is mounted)"}
+    import warnings
+    os.environ["AOED_REFERENCE_ROOT"] = root
+    try:
+        from oracle import ref_loader as rl
+        ns = rl.load()
+    except Exception as e:  # a dependency of the reference modules is missing on this box
+        return {"unavailable": f"reference modules do not import here: {type(e).__name__}: {e}"[:300]}
+    n_train = n_train or w["n_train"]
+    d, m, nu = w["n_var"], w["n_obj"], w["nu"]
+    X, Y, thetas = make_problem(n_train, d, m)
+    ctx, cores = blas_threads()
+    out = {"source": "unmodified autooed/mobo/surrogate_model/gp.py + acquisition/ucb.py on sklearn GaussianProcessRegressor",
+           "n_train": n_train, "cores": cores}
+    with ctx, warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = ns.GaussianProcess(rl.FakeProblem(d, m), nu=nu)
+        for g, th in zip(model.gps, thetas):
+            g.kernel = g.kernel.clone_with_theta(th)
+            g.optimizer = None
+        t0 = time.perf_counter()
+        model.fit(X, Y)
+        out["fit_fixed_theta_s"] = time.perf_counter() - t0
+        for g in model.gps:
+            g._K_inv = None  # sklearn >= 0.24 no longer defines the attribute gp.py:154 reads
+        acq = ns.UpperConfidenceBound(model)
+        acq.fit(X, Y)
+        Xs = candidates(rows, d, 2)
+        model.evaluate(Xs[:8], std=True)  # forms gp._K_inv once, as the reference caches it (gp.py:154-157)
+
+        def rate(fn, n):
+            t0 = time.perf_counter()
+            fn()
+            return n / (time.perf_counter() - t0)
+
+        out["evaluate_std_batched_per_s"] = rate(lambda: model.evaluate(Xs, std=True), rows)
+        out["evaluate_mean_gradient_batched_per_s"] = rate(lambda: model.evaluate(Xs, std=False, gradient=True), rows)
+        out["ucb_value_gradient_row_loop_per_s"] = rate(lambda: [acq.evaluate(Xs[i:i + 1], gradient=True) for i in range(loop_rows)], loop_rows)
+        g0 = model.gps[0]
+        t0 = time.perf_counter()
+        g0.log_marginal_likelihood(g0.kernel_.theta, eval_gradient=True)
+        out["sklearn_lml_gradient_call_s"] = time.perf_counter() - t0
+    out["sample"] = f"{rows} rows batched, {loop_rows} rows in the one-row loop, one LML + gradient call of one objective"
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -149,6 +205,10 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    try:
+        line["reference_literal"] = reference_literal(w)
+    except Exception as e:  # informational: never take the arm down
+        line["reference_literal"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     print(json.dumps(line), flush=True)
 
 
@@ -325,6 +385,12 @@ def run_ours(args):
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": blas_threads()[1], "kind": "port",
                                  "sample": f"{cpu_done} candidates of the same workload in {cpu_el:.1f}s (oracle/gp_oracle.py, numpy BLAS threads unrestricted)"},
                 "clocks": clocks, "device_host_legs_agree": same}
+        if world == 1 and args.extras == "all" and w is WORKLOADS["c4"]:
+            # SURVEY.md §8(d) B1 / B3 beside the port: the unmodified reference classes on sklearn (informational)
+            try:
+                line["cpu_baseline"]["reference_literal"] = reference_literal(w)
+            except Exception as e:
+                line["cpu_baseline"]["reference_literal"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
         line.update(extras)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
