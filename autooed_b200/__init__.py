@@ -7,7 +7,7 @@ All numerics run in libaoed_b200.so (hand-written CUDA, C ABI in include/aoed_b2
 from autooed_b200.surrogate_model import GaussianProcess
 from autooed_b200.acquisition import (Identity, UpperConfidenceBound, ExpectedImprovement, ProbabilityOfImprovement,
                                       ThompsonSampling)
-from autooed_b200.selection import HypervolumeImprovement, Uncertainty, Direct
+from autooed_b200.selection import HypervolumeImprovement, Uncertainty, Direct, Random
 from autooed_b200.solver import NSGA2
 from autooed_b200.acquisition.penalize import LocalPenalization, LocalLipschitzPenalization, HardLocalPenalization
 from autooed_b200.async_strategy import KrigingBeliever, LocalPenalizer, BelieverPenalizer

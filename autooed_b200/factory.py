@@ -6,13 +6,13 @@ from autooed_b200.acquisition import (Identity, UpperConfidenceBound, ExpectedIm
                                       ThompsonSampling)
 from autooed_b200.acquisition.penalize import LocalPenalization, LocalLipschitzPenalization, HardLocalPenalization
 from autooed_b200.async_strategy import KrigingBeliever, LocalPenalizer, BelieverPenalizer
-from autooed_b200.selection import HypervolumeImprovement, Uncertainty, Direct
+from autooed_b200.selection import HypervolumeImprovement, Uncertainty, Direct, Random
 from autooed_b200.solver import NSGA2, ParetoDiscovery
 
 _SURROGATES = {'gp': GaussianProcess}
 _ACQUISITIONS = {'ei': ExpectedImprovement, 'identity': Identity, 'pi': ProbabilityOfImprovement,
                  'ts': ThompsonSampling, 'ucb': UpperConfidenceBound}
-_SELECTIONS = {'direct': Direct, 'hvi': HypervolumeImprovement, 'uncertainty': Uncertainty}
+_SELECTIONS = {'direct': Direct, 'hvi': HypervolumeImprovement, 'random': Random, 'uncertainty': Uncertainty}
 _SOLVERS = {'nsga2': NSGA2, 'discovery': ParetoDiscovery}
 _ASYNC_ACQUISITIONS = {'lp': LocalPenalization, 'llp': LocalLipschitzPenalization, 'hlp': HardLocalPenalization}
 _ASYNC_STRATEGIES = {'kb': KrigingBeliever, 'lp': LocalPenalizer, 'bp': BelieverPenalizer}

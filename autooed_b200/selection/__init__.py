@@ -1,2 +1,2 @@
 from autooed_b200.selection.hvi import HypervolumeImprovement
-from autooed_b200.selection.simple import Direct, Uncertainty
+from autooed_b200.selection.simple import Direct, Random, Uncertainty

@@ -1,5 +1,6 @@
-"""The two selection rules of the reference that need no search: `Uncertainty` (`autooed/mobo/selection/uncertainty.py`,
-used by USeMO) and `Direct` (`autooed/mobo/selection/direct.py`, used when the solver already returns one batch)."""
+"""The selection rules of the reference that need no search: `Uncertainty` (`autooed/mobo/selection/uncertainty.py`,
+used by USeMO), `Direct` (`autooed/mobo/selection/direct.py`, used when the solver already returns one batch) and `Random`
+(`autooed/mobo/selection/random.py`)."""
 import numpy as np
 
 from autooed_b200.selection.base import Selection
@@ -27,3 +28,10 @@ class Direct(Selection):
         n = len(X_candidate)
         assert n == batch_size, f'Candidate size {n} != batch size {batch_size}, cannot use direct selection'
         return X_candidate
+
+
+class Random(Selection):
+    """Uniformly random batch without replacement; consumes the global numpy RNG exactly as the reference (random.py:15-17)."""
+
+    def _select(self, X_candidate, Y_candidate, X, Y, batch_size):
+        return X_candidate[np.random.choice(len(X_candidate), size=batch_size, replace=False)]

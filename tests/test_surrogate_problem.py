@@ -74,3 +74,17 @@ def test_real_acquisition_behind_the_adapter():
     assert np.array_equal(F, aF) and np.array_equal(dF, adF) and np.array_equal(hF, ahF)
     f1 = sp.evaluate(Xc[3])
     assert f1.shape == (2,) and np.allclose(f1, F[3], rtol=1e-12)
+
+
+def test_random_selection_consumes_the_global_rng_like_the_reference():
+    """`selection/random.py:15-17`: one `np.random.choice(n, size=batch, replace=False)`; registered as 'random' (factory.py:79)."""
+    from autooed_b200.factory import get_selection
+    from autooed_b200.selection import Random
+    assert get_selection('random') is Random
+    import types
+    Xc = np.arange(40.0).reshape(20, 2)
+    identity = types.SimpleNamespace(do=lambda A: np.asarray(A, float), undo=lambda A: np.asarray(A, float))
+    np.random.seed(4)
+    got = Random(types.SimpleNamespace(transformation=identity)).select(Xc, np.zeros((20, 2)), Xc[:3], np.zeros((3, 2)), 5)
+    np.random.seed(4)
+    assert np.array_equal(got, Xc[np.random.choice(20, size=5, replace=False)])
