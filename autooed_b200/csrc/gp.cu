@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -81,6 +82,7 @@ struct aoed_gp {
     int N = 0, Npad = 0, Kpad = 0, mTiles = 0, JS = 1, jchunk = 0;  // JS: CAPACITY of the training-index split (partials)
     int cap_Npad = 0;  // row capacity the device buffers were allocated for (re-used while N stays in the same 128-bucket)
     int occ_xcov = 2, occ_gradsum = 5;  // resident CTAs per SM of the two thread-per-candidate kernels
+    int blocked_cap_max = 1 << 30;       // problems per group the scratch budget allowed when it was last sized
     bool has_train = false, has_theta = false;
     std::vector<double> theta, y_mean, y_scale, lml, Xn, Yn;
     // device model state
@@ -806,6 +808,9 @@ int ensure_batch(aoed_gp* gp, int n_prob) {
 int ensure_blocked(aoed_gp* gp, int want) {
     const int Npad = gp->Npad, DP = gp->DP;
     if (gp->plan.T * TM != Npad) CHK(blocked_plan_build(gp->plan, Npad / TM));
+    // nothing to do when the scratch already serves `want` problems per group, or as many as the budget allowed last time
+    // (cudaMemGetInfo takes a device-wide lock: not something to call once per L-BFGS round)
+    if (gp->mats.Npad == Npad && gp->mats.cap >= std::min(std::max(want, 1), gp->blocked_cap_max)) return AOED_OK;
     const size_t per = 4 * size_t(Npad) * Npad * sizeof(double);
     const char* e = getenv("AOED_FIT_SCRATCH_GB");
     double budget = (e ? atof(e) : 16.0) * double(1ull << 30);
@@ -815,6 +820,7 @@ int ensure_blocked(aoed_gp* gp, int want) {
         budget = std::min(budget, 0.5 * (double(free_b) + held));
     }
     const int cap_max = std::max(1, int(budget / double(per)));
+    gp->blocked_cap_max = cap_max;
     const int cap = std::min(std::max(want, 1), cap_max);
     if (gp->mats.Npad == Npad && gp->mats.cap >= cap) return AOED_OK;
     blocked_mats_free(gp->mats);
@@ -946,6 +952,8 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
     if (!gp || !h_obj || !h_theta || !h_lml) return fail(AOED_ERR_INVALID, "null argument");
     if (!gp->has_train) return fail(AOED_ERR_INVALID, "set_train must be called first");
     if (n_prob <= 0) return AOED_OK;
+    static const bool fit_timing = getenv("AOED_FIT_TIMING") != nullptr;
+    const auto t_call = std::chrono::steady_clock::now();
     DeviceGuard guard_(gp->device);
     CU(guard_.err);
     const int N = gp->N, Npad = gp->Npad, m = gp->m, d = gp->d, p = d + 2, DP = gp->DP;
@@ -996,6 +1004,7 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
         // blocked factorisation, all problems of a group side by side in every launch (blocked.cu)
         CHK(ensure_blocked(gp, n_prob));
         const int cap = gp->mats.cap;
+        if (fit_timing) CU(cudaEventRecord(gp->ev0, s0));
         for (int g0 = 0; g0 < n_prob; g0 += cap) {
             const int G = std::min(cap, n_prob - g0);
             double* res = gp->dResB + size_t(g0) * (p + 1);
@@ -1022,7 +1031,14 @@ int aoed_gp_lml_batch(aoed_gp_t* gp, int n_prob, const int32_t* h_obj, const dou
     }
     std::vector<double> res(size_t(n_prob) * (p + 1));
     CU(cudaMemcpyAsync(res.data(), gp->dResB, res.size() * sizeof(double), cudaMemcpyDeviceToHost, s0));
+    if (fit_timing && !small) CU(cudaEventRecord(gp->ev1, s0));
     CU(cudaStreamSynchronize(s0));
+    if (fit_timing && !small) {  // AOED_FIT_TIMING=1: device time of the round (events) beside the host's wall time of the call
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, gp->ev0, gp->ev1);
+        const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
+        fprintf(stderr, "[fit timing] problems %d device %.2f ms call %.2f ms\n", n_prob, double(ms), wall);
+    }
     for (int b = 0; b < n_prob; ++b) {
         h_lml[b] = res[size_t(b) * (p + 1)];
         if (want_grad)
