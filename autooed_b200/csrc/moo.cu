@@ -756,10 +756,10 @@ int aoed_pareto_rank(int device, int64_t n, int m, const double* h_Y, int32_t* h
     if (rc != AOED_OK) return rc;
     const char* force = getenv("AOED_RANK_PATH");  // "multi" forces the multi-launch path (tests)
     if (!(force && strcmp(force, "multi") == 0) && n <= RS_MAX_N &&
-        size_t(m) * n * sizeof(double) + 3 * size_t(n) * sizeof(int) <= 200 * 1024) {
+        aoed::rank_small_smem(m, int(n)) <= 200 * 1024) {
         // one launch: the call is latency bound (it runs once per NSGA-II generation of the host loop)
         int32_t* drank;
-        MCHK(ws_get(w, WS_IDX, (1 + aoed::DC_SPLIT) * size_t(n), &drank));
+        MCHK(ws_get(w, WS_IDX, size_t(n) + aoed::rank_scratch_ints(int(n)), &drank));
         rc = launch_rank_small(m, dYT, int(n), drank, drank + n, nullptr);
         if (rc != AOED_OK) return rc;
         MCU(cudaMemcpy(h_rank, drank, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToHost));

@@ -454,7 +454,7 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
     NCU(cudaMalloc(&bYT.p, size_t(cap + P) * m * sizeof(double)));
     NCU(cudaMalloc(&bRank.p, size_t(cap + P) * sizeof(int)));
     NCU(cudaMalloc(&bCrowd.p, size_t(cap + P) * sizeof(double)));
-    NCU(cudaMalloc(&bCnt.p, size_t(cap + P) * DC_SPLIT * sizeof(int)));
+    NCU(cudaMalloc(&bCnt.p, rank_scratch_ints(int(cap + P)) * sizeof(int)));
     NCU(cudaMalloc(&bSel.p, size_t(cap) * sizeof(int)));
     NCU(cudaMalloc(&bXl.p, d * sizeof(double)));
     NCU(cudaMalloc(&bXu.p, d * sizeof(double)));
@@ -635,7 +635,7 @@ extern "C" int aoed_nsga2_survival(int device, int64_t n64, int n_obj, const dou
     NBuf bYT, bRank, bCnt, bLast, bCrowd, bSel;
     NCU(cudaMalloc(&bYT.p, yt.size() * sizeof(double)));
     NCU(cudaMalloc(&bRank.p, size_t(n) * sizeof(int)));
-    NCU(cudaMalloc(&bCnt.p, size_t(n) * DC_SPLIT * sizeof(int)));
+    NCU(cudaMalloc(&bCnt.p, rank_scratch_ints(n) * sizeof(int)));
     NCU(cudaMalloc(&bLast.p, sizeof(int)));
     NCU(cudaMalloc(&bCrowd.p, size_t(n) * sizeof(double)));
     NCU(cudaMalloc(&bSel.p, size_t(keep) * sizeof(int)));

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace aoed {
 
@@ -24,6 +25,7 @@ __device__ __forceinline__ int warp_slot(int* ctr, bool pred) {
     return pred ? base + __popc(mask & ((1u << lane) - 1u)) : -1;
 }
 constexpr int RS_MAX_N = 4096;
+constexpr int RS_PT = RS_MAX_N / RS_THREADS;  // points per thread of the one-CTA sort
 
 // domination counts of all n points over many CTAs: a warp owns 32 consecutive points; the candidates for "dominates
 // it" are cut into DC_SPLIT contiguous slices (grid.y), staged in shared memory — read straight from global memory every
@@ -76,98 +78,120 @@ __global__ void __launch_bounds__(RS_THREADS) rank_small_kernel(const double* __
                                                                 const int* __restrict__ cnt_in, int need,
                                                                 int* __restrict__ last_rank_out) {
     extern __shared__ double rs_smem[];
-    double* Y = rs_smem;                                   // [M][n]
-    int* cnt = reinterpret_cast<int*>(Y + size_t(M) * n);  // [n] number of not-yet-peeled points dominating i
-    int* rk = cnt + n;                                     // [n]
-    int* front = rk + n;                                   // [n] compacted current front
-    __shared__ int n_front, n_left, last_full;
+    double* Y = rs_smem;                                    // [M][n]
+    int* list0 = reinterpret_cast<int*>(Y + size_t(M) * n); // [n] compacted fronts, alternating: the one being peeled ...
+    int* list1 = list0 + n;                                 // [n] ... and the one that forms while it is peeled
+    __shared__ int n_list[3];  // member counts, rotating: read in round r, filled in round r (for r + 1), cleared for r + 2
     const int tid = threadIdx.x;
     for (int i = tid; i < M * n; i += RS_THREADS) Y[i] = YT[i];
-    if (tid == 0) {
-        n_left = n;
-        last_full = 0;
-    }
+    if (tid < 3) n_list[tid] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += RS_THREADS) {
-        int c = 0;
-        if (cnt_in) {
+    // A thread owns the points tid, tid + 1024, ... (at most RS_PT): their coordinates, remaining-dominator counts and ranks
+    // stay in registers for the whole sort; shared memory holds the coordinate table and the front lists only.
+    // (1024 threads leave 64 registers each: the coordinates are cached for up to four objectives, read from shared memory beyond)
+    constexpr bool CACHE = M <= 4;
+    double yq[CACHE ? RS_PT : 1][M];
+    int cnt[RS_PT], rk[RS_PT];
 #pragma unroll
-            for (int y = 0; y < DC_SPLIT; ++y) c += cnt_in[y * n + i];
-        } else {
-            double yi[M];
+    for (int u = 0; u < RS_PT; ++u) {  // domination counts; the points nobody dominates are front 0
+        const int i = u * RS_THREADS + tid;
+        int c = 1;
+        if (i < n) {
+            if (CACHE) {
 #pragma unroll
-            for (int k = 0; k < M; ++k) yi[k] = Y[k * n + i];
-            for (int j = 0; j < n; ++j) {
-                bool le = true, lt = false;
+                for (int k = 0; k < M; ++k) yq[u][k] = Y[k * n + i];
+            }
+            c = 0;
+            if (cnt_in) {
 #pragma unroll
-                for (int k = 0; k < M; ++k) {
-                    const double v = Y[k * n + j];
-                    le = le && (v <= yi[k]);
-                    lt = lt || (v < yi[k]);
+                for (int y = 0; y < DC_SPLIT; ++y) c += cnt_in[y * n + i];
+            } else {
+                for (int j = 0; j < n; ++j) {
+                    bool le = true, lt = false;
+#pragma unroll
+                    for (int k = 0; k < M; ++k) {
+                        const double v = Y[k * n + j], mine = CACHE ? yq[u][k] : Y[k * n + i];
+                        le = le && (v <= mine);
+                        lt = lt || (v < mine);
+                    }
+                    c += (le && lt) ? 1 : 0;
                 }
-                c += (le && lt) ? 1 : 0;
             }
         }
-        cnt[i] = c;
-        rk[i] = -1;
+        cnt[u] = c;
+        rk[u] = c == 0 ? 0 : -1;
+        if (u * RS_THREADS < n) {  // uniform over the CTA
+            const int slot = warp_slot(&n_list[0], i < n && c == 0);
+            if (i < n && c == 0) list0[slot] = i;
+        }
     }
-    __syncthreads();
-    for (int r = 0; n_left > 0; ++r) {
-        if (tid == 0) n_front = 0;
+    // Peeling.  ONE barrier per front: while front r is subtracted from the counts of the points it dominates, a point whose
+    // count reaches 0 IS a member of front r + 1 and appends itself to the other list — no separate scan for the next front.
+    // (Early NSGA-II generations have hundreds of fronts of a few members each: the cost of a sort is the cost per front.)
+    int left = n, last_full = 0;  // uniform over the CTA: every thread follows the same counts
+    for (int r = 0;; ++r) {
         __syncthreads();
-        for (int i0 = 0; i0 < n; i0 += RS_THREADS) {
-            const int i = i0 + tid;
-            const bool in_front = i < n && rk[i] < 0 && cnt[i] == 0;
-            const int slot = warp_slot(&n_front, in_front);
-            if (in_front) {
-                rk[i] = r;
-                front[slot] = i;
-            }
-        }
-        __syncthreads();
-        const int nf = n_front;
-        if (nf == 0) break;  // cannot happen for finite inputs (a minimal element always exists); NaN rows stay at -1
-        if (n - n_left + nf >= need && nf < n_left) {  // enough ranked: everything left shares the next rank number
-            for (int i = tid; i < n; i += RS_THREADS)
-                if (rk[i] < 0) rk[i] = r + 1;
-            if (tid == 0) last_full = r;
-            __syncthreads();
+        const int nf = n_list[r % 3];
+        if (nf == 0) break;  // with points left: only for non-finite inputs (a finite set always has a minimal element)
+        if (n - left + nf >= need && nf < left) {  // enough ranked: everything left shares the next rank number
+#pragma unroll
+            for (int u = 0; u < RS_PT; ++u)
+                if (rk[u] < 0) rk[u] = r + 1;
+            last_full = r;
             break;
         }
-        if (tid == 0) last_full = r;
-        for (int q = tid; q < n; q += RS_THREADS) {
-            if (rk[q] >= 0) continue;
-            double yq[M];
+        last_full = r;
+        left -= nf;
+        if (left == 0) break;
+        if (tid == 0) n_list[(r + 2) % 3] = 0;  // last read a round ago (every thread has passed this round's barrier since)
+        const int* front = (r & 1) ? list1 : list0;
+        int* next = (r & 1) ? list0 : list1;
 #pragma unroll
-            for (int k = 0; k < M; ++k) yq[k] = Y[k * n + q];
-            int dec = 0;
-            for (int t = 0; t < nf; ++t) {
-                const int pidx = front[t];
-                bool le = true, lt = false;
+        for (int u = 0; u < RS_PT; ++u) {
+            if (u * RS_THREADS >= n) break;  // uniform
+            const int q = u * RS_THREADS + tid;
+            bool joins = false;
+            if (q < n && rk[u] < 0) {
+                int dec = 0;
+                for (int t = 0; t < nf; ++t) {
+                    const int pidx = front[t];
+                    bool le = true, lt = false;
 #pragma unroll
-                for (int k = 0; k < M; ++k) {
-                    const double v = Y[k * n + pidx];
-                    le = le && (v <= yq[k]);
-                    lt = lt || (v < yq[k]);
+                    for (int k = 0; k < M; ++k) {
+                        const double v = Y[k * n + pidx], mine = CACHE ? yq[u][k] : Y[k * n + q];
+                        le = le && (v <= mine);
+                        lt = lt || (v < mine);
+                    }
+                    dec += (le && lt) ? 1 : 0;
                 }
-                dec += (le && lt) ? 1 : 0;
+                cnt[u] -= dec;
+                if (cnt[u] == 0) {
+                    rk[u] = r + 1;
+                    joins = true;
+                }
             }
-            cnt[q] -= dec;
+            const int slot = warp_slot(&n_list[(r + 1) % 3], joins);
+            if (joins) next[slot] = q;
         }
-        __syncthreads();
-        if (tid == 0) n_left -= nf;
-        __syncthreads();
     }
-    for (int i = tid; i < n; i += RS_THREADS) rank_out[i] = rk[i];
+#pragma unroll
+    for (int u = 0; u < RS_PT; ++u) {
+        const int i = u * RS_THREADS + tid;
+        if (i < n) rank_out[i] = rk[u];
+    }
     if (last_rank_out && tid == 0) *last_rank_out = last_full;  // highest rank whose front was peeled completely
 }
 
 
-inline size_t rank_small_smem(int m, int n) { return size_t(m) * n * sizeof(double) + 3 * size_t(n) * sizeof(int); }
+// device ints the rank launchers need as scratch for n points (the DC_SPLIT partial counts)
+inline size_t rank_scratch_ints(int n) { return size_t(DC_SPLIT) * n; }
+
+inline size_t rank_small_smem(int m, int n) { return size_t(m) * n * sizeof(double) + 2 * size_t(n) * sizeof(int); }
 constexpr int RS_SPLIT_N = 1024;  // above this the domination counts come from dom_count_kernel
 
-// launches the sort of n <= RS_MAX_N points on stream s; `cnt_scratch` ([DC_SPLIT * n] ints on the device) enables the split
-// counting for large n (pass nullptr to stay with the single kernel)
+// launches the sort of n <= RS_MAX_N points on stream s; `cnt_scratch` ([rank_scratch_ints(n)] ints on the device) enables the
+// split
+// counting over many CTAs for large n (pass nullptr to stay with the single kernel)
 constexpr size_t RS_SMEM_LIMIT = 200 * 1024;  // callers check rank_small_smem(m, n) against this
 
 template <int M>
