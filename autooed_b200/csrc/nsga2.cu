@@ -103,6 +103,8 @@ __device__ __forceinline__ double poly_mutate(double x, double lo, double hi, do
 // the start of the pair's Philox subsequence and are replayed by each of its threads; variable k owns the 64 draws at
 // offset 64 (k + 1) of the same subsequence, so the result does not depend on how the work is spread over threads.
 __global__ void __launch_bounds__(128) variation_kernel(VarArgs p) {
+    pdl_wait();
+    pdl_trigger();
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int pair = gid / p.d, k = gid - pair * p.d;
     if (2 * pair >= p.P) return;
@@ -236,6 +238,8 @@ __device__ int stage_relevant(const int* __restrict__ rank, int n, int last, int
 // the order a stable sort gives.  ~10 instructions per pair; the neighbour lookups happen in select_kernel.
 __global__ void __launch_bounds__(32 * CW_WARPS) crowd_pos_kernel(SurvivalTables p) {
     extern __shared__ double cw_smem[];
+    pdl_wait();
+    pdl_trigger();
     const int n = p.n;
     double* fs = cw_smem;                      // [nr] objective k of the relevant individuals
     int* rs = reinterpret_cast<int*>(fs + n);  // [nr] ranks
@@ -321,6 +325,8 @@ struct SelectArgs {
 
 __global__ void __launch_bounds__(32 * CW_WARPS) select_kernel(SelectArgs p) {
     extern __shared__ double cw_smem[];
+    pdl_wait();
+    pdl_trigger();
     const int n = p.tab.n;
     double* cs = cw_smem;                      // [nr] crowding distances of the relevant individuals
     int* rs = reinterpret_cast<int*>(cs + n);  // [nr] ranks
@@ -395,10 +401,11 @@ struct SurvivalScratch {
     }
 };
 
-int launch_rank(int m, const double* YT, int n, int32_t* rank, int* cnt_scratch, int need, int* last_rank, cudaStream_t s) {
-#define NS_RANK_CASE(MM)                                                              \
-    case MM:                                                                          \
-        NCU(launch_rank_small_m<MM>(YT, n, rank, cnt_scratch, need, s, last_rank));   \
+int launch_rank(int m, const double* YT, int n, int32_t* rank, int* cnt_scratch, int need, int* last_rank, cudaStream_t s,
+                bool pdl = false) {
+#define NS_RANK_CASE(MM)                                                                   \
+    case MM:                                                                               \
+        NCU(launch_rank_small_m<MM>(YT, n, rank, cnt_scratch, need, s, last_rank, pdl));   \
         break;
     switch (m) {
         NS_RANK_CASE(1) NS_RANK_CASE(2) NS_RANK_CASE(3) NS_RANK_CASE(4) NS_RANK_CASE(5) NS_RANK_CASE(6) NS_RANK_CASE(7) NS_RANK_CASE(8)
@@ -471,6 +478,9 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
 
     // AOED_NSGA2_STAMP=1: CUDA events between the phases of every generation, per-phase totals on stderr (diagnostics)
     const bool stamp = getenv("AOED_NSGA2_STAMP") != nullptr;
+    // AOED_NSGA2_PDL=0: ordinary stream serialisation between the kernels of a generation instead of programmatic dependent launch
+    const char* pdl_env = getenv("AOED_NSGA2_PDL");
+    const bool pdl = !stamp && !(pdl_env && pdl_env[0] == '0');
     std::vector<std::pair<int, cudaEvent_t>> marks;
     auto mark = [&](int phase) {
         if (!stamp) return;
@@ -488,17 +498,17 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
     auto survive = [&](int src, int na, const double* Xb, const double* Fb, const uint8_t* dup, int nb, int keep, int dst) -> int {
         const int n = na + nb;
         merge_kernel<<<(n + 255) / 256, 256, 0, s>>>(bF[src].as<double>(), na, Fb, dup, nb, m, bYT.as<double>());
-        NCHK(launch_rank(m, bYT.as<double>(), n, bRank.as<int>(), bCnt.as<int>(), keep, bLast.as<int>(), s));
+        NCHK(launch_rank(m, bYT.as<double>(), n, bRank.as<int>(), bCnt.as<int>(), keep, bLast.as<int>(), s, pdl));
         mark(4);
         SelectArgs sa;
         sa.tab = scratch.tables(bYT.as<double>(), bRank.as<int>(), bLast.as<int>(), n, m);
-        crowd_pos_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n), s>>>(sa.tab);
+        NCU(launch_pdl(pdl, crowd_pos_kernel, dim3((n + 31) / 32), dim3(32 * CW_WARPS), crowd_smem(n), s, sa.tab));
         mark(5);
         sa.crowd = bCrowd.as<double>();
         sa.Xpop = bX[src].as<double>(); sa.Fpop = bF[src].as<double>(); sa.Xoff = Xb; sa.Foff = Fb;
         sa.n_cur = na; sa.keep = keep; sa.d = d; sa.sel = bSel.as<int>();
         sa.Xnew = bX[dst].as<double>(); sa.Fnew = bF[dst].as<double>(); sa.cnew = bC[dst].as<double>(); sa.rnew = bR[dst].as<int>();
-        select_kernel<<<(n + 31) / 32, 32 * CW_WARPS, crowd_smem(n), s>>>(sa);
+        NCU(launch_pdl(pdl, select_kernel, dim3((n + 31) / 32), dim3(32 * CW_WARPS), crowd_smem(n), s, sa));
         mark(6);
         NCU(cudaGetLastError());
         return AOED_OK;
@@ -539,7 +549,7 @@ int nsga2_core(int device, int n_var, int n_obj, const Evaluator& eval_fn, int64
         va.xl = bXl.as<double>(); va.xu = bXu.as<double>(); va.Xoff = bXoff.as<double>(); va.Xn = bXn.as<double>();
         va.n_cur = n_cur; va.P = P; va.d = d; va.seed = seed; va.gen = bGen.as<int>(); va.pc = 0.9; va.eta_c = 15.0; va.eta_m = 20.0;
         mark(0);
-        variation_kernel<<<((P + 1) / 2 * d + 127) / 128, 128, 0, s>>>(va);
+        NCU(launch_pdl(pdl, variation_kernel, dim3(((P + 1) / 2 * d + 127) / 128), dim3(128), 0, s, va));
         mark(1);
         cudaStream_t sdup = serial ? s : s2;
         if (!serial) {

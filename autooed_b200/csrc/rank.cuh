@@ -8,6 +8,29 @@
 
 namespace aoed {
 
+// Programmatic dependent launch (PDL): a kernel launched with `launch_pdl` may be scheduled while its predecessor in the stream
+// is still running; it must call pdl_wait() before it touches anything the predecessor wrote (the wait returns once the
+// predecessor grid has completed and its writes are visible).  pdl_trigger() in the predecessor allows that early scheduling.
+// Both are no-ops in a kernel launched the ordinary way.  In the NSGA-II generation loop this hides the launch latency of the
+// short kernels that follow each other (~2 us per boundary).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Whole non-dominated sort in ONE CTA for populations that fit in shared memory (the NSGA-II regime, n <= 4096):
 // domination counts, then front peeling with the counts decremented by the members of each peeled front — no host
 // round trip per front.  Same semantics as the multi-launch path below (rank = front number, pymoo NonDominatedSorting).
@@ -39,6 +62,8 @@ template <int M>
 __global__ void __launch_bounds__(32 * DC_WARPS) dom_count_kernel(const double* __restrict__ YT, int n, int chunk, int* __restrict__ cnt) {
     extern __shared__ double dc_smem[];  // [M][chunk]
     __shared__ int part[32];
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = blockIdx.x * 32 + lane;
     const int j0 = blockIdx.y * chunk, len = min(chunk, n - j0);
     for (int t = threadIdx.x; t < M * chunk; t += 32 * DC_WARPS) {
@@ -83,6 +108,8 @@ __global__ void __launch_bounds__(RS_THREADS) rank_small_kernel(const double* __
     int* list1 = list0 + n;                                 // [n] ... and the one that forms while it is peeled
     __shared__ int n_list[3];  // member counts, rotating: read in round r, filled in round r (for r + 1), cleared for r + 2
     const int tid = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     for (int i = tid; i < M * n; i += RS_THREADS) Y[i] = YT[i];
     if (tid < 3) n_list[tid] = 0;
     __syncthreads();
@@ -196,7 +223,7 @@ constexpr size_t RS_SMEM_LIMIT = 200 * 1024;  // callers check rank_small_smem(m
 
 template <int M>
 cudaError_t launch_rank_small_m(const double* YT, int n, int32_t* rank, int* cnt_scratch, int need, cudaStream_t s,
-                                int* last_rank_out = nullptr) {
+                                int* last_rank_out = nullptr, bool pdl = false) {
     const size_t sm = rank_small_smem(M, n);
     const int chunk = dom_count_chunk(n);
     const size_t dsm = size_t(M) * chunk * sizeof(double);
@@ -214,10 +241,12 @@ cudaError_t launch_rank_small_m(const double* YT, int n, int32_t* rank, int* cnt
     }
     const int* cnt_in = nullptr;
     if (cnt_scratch && n > RS_SPLIT_N) {
-        dom_count_kernel<M><<<dim3((n + 31) / 32, DC_SPLIT), 32 * DC_WARPS, dsm, s>>>(YT, n, chunk, cnt_scratch);
+        e = launch_pdl(pdl, dom_count_kernel<M>, dim3((n + 31) / 32, DC_SPLIT), dim3(32 * DC_WARPS), dsm, s, YT, n, chunk, cnt_scratch);
+        if (e != cudaSuccess) return e;
         cnt_in = cnt_scratch;
     }
-    rank_small_kernel<M><<<1, RS_THREADS, sm, s>>>(YT, n, rank, cnt_in, need, last_rank_out);
+    e = launch_pdl(pdl, rank_small_kernel<M>, dim3(1), dim3(RS_THREADS), sm, s, YT, n, rank, cnt_in, need, last_rank_out);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
