@@ -153,3 +153,46 @@ def test_graph_replay_equals_stream_launches(acq_name, monkeypatch):
             np.random.seed(9)
             out[mode] = NSGA2(prob, n_gen=n_gen, pop_size=64).solve(X, Y, 8, acq)
         assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
+
+
+def test_generation_graph_variants_give_identical_runs(tmp_path):
+    """The replayed graph of a generation runs the duplicate scan as a branch parallel to the evaluator and launches the kernels
+    that follow each other directly as programmatic dependents (csrc/nsga2.cu).  Both are scheduling only: with them switched
+    off (AOED_NSGA2_FORK=0, AOED_NSGA2_PDL=0: one serial stream, ordinary launches) and with plain stream launches instead of
+    the graph (AOED_NSGA2_GRAPH=0) the same seed must give the same final population bit for bit — identity acquisition at
+    pop 200 (one-CTA sort) and EI at pop 1100 (many-CTA counting + one-CTA peeling).  The switches are latched per
+    process: child processes."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = f"""
+import sys, numpy as np
+sys.path[:0] = [{here!r}, {os.path.dirname(here)!r}]
+import autooed_b200 as ab
+from autooed_b200.problem import SimpleProblem
+from autooed_b200.solver import NSGA2
+rng = np.random.default_rng(1)
+d, m, N = 5, 2, 40
+X = rng.random((N, d)); Y = np.stack([X[:, 0], 1 + X[:, 1:].sum(1) - np.sqrt(X[:, 0])], 1)
+prob = SimpleProblem(d, m)
+sur = ab.GaussianProcess(prob, nu=5); sur.fit(X, Y)
+out = {{}}
+for name, pop in (("identity", 200), ("ei", 1100)):
+    acq = ab.get_acquisition(name)(sur); acq.fit(X, Y)
+    np.random.seed(3)
+    solver = NSGA2(prob, n_gen=40, pop_size=pop)
+    Xc, Fc = solver.solve(X, Y, 8, acq)
+    out[name + "_X"], out[name + "_F"] = Xc, Fc
+np.savez(sys.argv[1], **out)
+"""
+    runs = {}
+    for tag, env in (("default", {}), ("serial", {"AOED_NSGA2_FORK": "0", "AOED_NSGA2_PDL": "0"}), ("stream", {"AOED_NSGA2_GRAPH": "0"})):
+        path = str(tmp_path / f"{tag}.npz")
+        r = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr[-2000:]
+        runs[tag] = dict(np.load(path))
+    for tag in ("serial", "stream"):
+        for k, v in runs["default"].items():
+            assert np.array_equal(runs[tag][k], v), (tag, k)
+    assert len(runs["default"]["ei_X"]) > 0
