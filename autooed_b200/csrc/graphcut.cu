@@ -12,8 +12,11 @@
 //   cycles repeat until one brings no decrease or n_iter cycles are done (n_iter < 0: until convergence, 0: no move).
 //   Every pair term must be submodular for the move:  V(fi,fj) + V(a,a) <= V(fi,a) + V(a,fj)  (true for the reference's
 //   V = -C_inf * I); a violating pair is reported as AOED_ERR_UNSUPPORTED instead of being truncated.
-//   Of the minimum cuts the one with the SMALLEST source side is taken (nodes reachable from the source in the residual
-//   graph keep their label), which is unique — so a tie never moves a node, and any correct max-flow gives the same result.
+//   Of the minimum cuts the one with the SMALLEST sink side is taken (only the nodes that can still reach the sink in the
+//   residual graph take alpha): that set is unique — any correct max-flow gives the same result — and it is empty whenever
+//   keeping every label is already optimal, so a tie never moves a node and every accepted move lowers the energy strictly.
+//   Two exact shortcuts keep the number of max-flows small: a label is not tried again while the labeling has not changed
+//   since its last fruitless attempt, and not at all when an upper bound on its gain (term by term) is zero.
 // Max-flow: Dinic's algorithm with BFS levels and iterative DFS on a CSR-like arc list.
 #include <algorithm>
 #include <cstdint>
@@ -32,11 +35,17 @@ struct FlowGraph {
         int to, next;
         int64_t cap;
     };
-    std::vector<int> head, level, it;
+    std::vector<int> head, level, it, queue, path;  // (queue / path: scratch of bfs / augment, kept to avoid re-allocation)
     std::vector<Arc> arcs;
     int s, t;
 
-    explicit FlowGraph(int n_inner) : head(n_inner + 2, -1), level(n_inner + 2), it(n_inner + 2), s(n_inner), t(n_inner + 1) {}
+    explicit FlowGraph(int n_inner) : head(n_inner + 2, -1), level(n_inner + 2), it(n_inner + 2), s(n_inner), t(n_inner + 1) {
+        queue.reserve(n_inner + 2);
+    }
+    void reset() {  // same nodes, no arcs: one object serves every move
+        std::fill(head.begin(), head.end(), -1);
+        arcs.clear();
+    }
 
     void add(int u, int v, int64_t c_uv, int64_t c_vu) {
         arcs.push_back({v, head[u], c_uv});
@@ -46,8 +55,7 @@ struct FlowGraph {
     }
     bool bfs() {
         std::fill(level.begin(), level.end(), -1);
-        std::vector<int> queue;
-        queue.reserve(head.size());
+        queue.clear();
         queue.push_back(s);
         level[s] = 0;
         for (size_t qi = 0; qi < queue.size(); ++qi) {
@@ -62,7 +70,7 @@ struct FlowGraph {
     }
     // one augmenting path along the level graph, iteratively; returns the flow pushed (0: none left)
     int64_t augment() {
-        std::vector<int> path;  // arcs from s
+        path.clear();  // arcs from s
         int u = s;
         for (;;) {
             if (u == t) {
@@ -95,8 +103,25 @@ struct FlowGraph {
         }
         return flow;
     }
-    // after max_flow(): level[] of the last (failed) BFS marks the nodes reachable from s in the residual graph
-    bool source_side(int u) const { return level[u] >= 0; }
+    // after max_flow(): marks (in level[], 1 / 0) the nodes that can reach t through arcs with residual capacity —
+    // the sink side of the minimum cut whose sink side is smallest
+    void mark_sink_side() {
+        std::fill(level.begin(), level.end(), 0);
+        queue.clear();
+        queue.push_back(t);
+        level[t] = 1;
+        for (size_t qi = 0; qi < queue.size(); ++qi) {
+            const int v = queue[qi];
+            for (int b = head[v]; b >= 0; b = arcs[b].next) {
+                const int u = arcs[b].to;  // arc u -> v is the partner of b
+                if (!level[u] && arcs[b ^ 1].cap > 0) {
+                    level[u] = 1;
+                    queue.push_back(u);
+                }
+            }
+        }
+    }
+    bool sink_side(int u) const { return level[u] != 0; }
 };
 
 int64_t energy_of(int n_node, int64_t n_edge, const int32_t* edges, int n_label, const int32_t* unary, const int32_t* pairwise,
@@ -122,17 +147,30 @@ extern "C" int aoed_graph_cut(int n_node, int64_t n_edge, const int32_t* edges, 
     int64_t e_cur = energy_of(n_node, n_edge, edges, n_label, unary, pairwise, labels);
     auto V = [&](int a, int b) -> int64_t { return pairwise[int64_t(a) * n_label + b]; };
     std::vector<int64_t> c0(n_node), c1(n_node);  // unary cost of x = 0 (keep) and x = 1 (take alpha), pair terms folded in
+    std::vector<long long> tried_at(n_label, -1);  // labeling version at the label's last fruitless attempt
+    long long version = 0;                         // bumped by every accepted move
+    FlowGraph g(n_node);
     for (int cycle = 0; n_iter < 0 || cycle < n_iter; ++cycle) {
         const int64_t e_before = e_cur;
         for (int alpha = 0; alpha < n_label; ++alpha) {
+            if (tried_at[alpha] == version) continue;  // same labeling as last time: the same (empty) move
+            tried_at[alpha] = version;
+            // upper bound on what the move can gain, term by term
+            int64_t gain = 0;
             bool any_other = false;
             for (int i = 0; i < n_node; ++i) {
                 c0[i] = unary[int64_t(i) * n_label + labels[i]];
                 c1[i] = unary[int64_t(i) * n_label + alpha];
+                gain += std::max<int64_t>(0, c0[i] - c1[i]);
                 any_other = any_other || labels[i] != alpha;
             }
             if (!any_other) continue;
-            FlowGraph g(n_node);
+            for (int64_t k = 0; k < n_edge && gain == 0; ++k) {
+                const int lp = labels[edges[2 * k]], lq = labels[edges[2 * k + 1]];
+                gain += std::max<int64_t>(0, V(lp, lq) - std::min(V(alpha, alpha), std::min(V(lp, alpha), V(alpha, lq))));
+            }
+            if (gain == 0) continue;
+            g.reset();
             for (int64_t k = 0; k < n_edge; ++k) {
                 const int p = edges[2 * k], q = edges[2 * k + 1];
                 // E(xp, xq): A = (0,0), B = (0,1), C = (1,0), D = (1,1)
@@ -151,13 +189,17 @@ extern "C" int aoed_graph_cut(int n_node, int64_t n_edge, const int32_t* edges, 
                 if (c0[i] - lo > 0) g.add(i, g.t, c0[i] - lo, 0);  // cut when i is on the source side: x = 0
             }
             g.max_flow();
+            g.mark_sink_side();
             bool moved = false;
             for (int i = 0; i < n_node; ++i)
-                if (!g.source_side(i) && labels[i] != alpha) {
+                if (g.sink_side(i) && labels[i] != alpha) {
                     labels[i] = alpha;
                     moved = true;
                 }
-            if (moved) e_cur = energy_of(n_node, n_edge, edges, n_label, unary, pairwise, labels);
+            if (moved) {
+                ++version;
+                e_cur = energy_of(n_node, n_edge, edges, n_label, unary, pairwise, labels);
+            }
         }
         if (e_cur >= e_before) break;
     }

@@ -192,7 +192,7 @@ int aoed_hv_contributions(int device, int64_t n_cand, int m, const double* h_Yc,
  * autooed/mobo/solver/pareto_discovery/buffer.py:249 (alpha-expansion graph cut, gco-v3.0 behind a Cython wrapper):
  *   minimises  E(l) = sum_i unary[i][l_i] + sum_{(i,j) in edges} pairwise[l_i][l_j]
  * over labelings of n_node nodes with n_label labels, starting from label 0 everywhere, by cycles of expansion moves
- * (alpha = 0 .. n_label-1 in order, each move an exact minimum s-t cut, the minimum cut with the smallest source side so
+ * (alpha = 0 .. n_label-1 in order, each move an exact minimum s-t cut, the minimum cut with the smallest sink side so
  * that ties never move a node); stops after a cycle without decrease or after n_iter cycles (n_iter < 0: until convergence).
  *   edges (n_edge x 2, node indices), unary (n_node x n_label), pairwise (n_label x n_label): int32 as pygco requires;
  *   labels (n_node) out; energy (may be NULL) = E of the returned labeling.

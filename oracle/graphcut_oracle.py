@@ -6,9 +6,9 @@ argument of that function is `n_iter`, so the reference's `label_cost` is in fac
 of gco-v3.0 — is a third-party dependency that is neither in /root/reference nor installable here: PARITY UNPINNED against the
 library itself.  What is restated is the published algorithm (alpha-expansion, Boykov / Veksler / Zabih 2001, with the binary
 moves solved exactly as minimum cuts, Kolmogorov & Zabih 2004), and it is anchored three ways:
-  * `expansion`           the algorithm on networkx's `edmonds_karp` (an independent max-flow; the nodes reachable from the source
-                          in its residual network are the same unique minimal source side the product's routine takes), same
-                          label order and stopping rule;
+  * `expansion`           the algorithm on networkx's `edmonds_karp` (an independent max-flow; the nodes that can reach the sink
+                          in its residual network are the same unique minimal sink side the product's routine takes), same
+                          label order and stopping rule, no shortcuts;
   * `brute_force`         the global optimum by enumeration (small graphs): a two-label expansion from label 0 must reach it;
   * `is_expansion_optimal` no single expansion move (enumerated) improves the result.
 """
@@ -57,19 +57,19 @@ def _move(edges, unary, pairwise, labels, alpha):
             arc('s', i, int(c1[i] - lo))
         if c0[i] > lo:
             arc(i, 't', int(c0[i] - lo))
-    # the SMALLEST source side of a minimum cut = the nodes reachable from s in the residual network of any maximum flow
-    # (nx.minimum_cut returns the other extreme, the smallest sink side)
+    # the SMALLEST sink side of a minimum cut = the nodes that can still reach t in the residual network of any maximum flow
+    # (what nx.minimum_cut returns as its second set); it is empty when keeping every label is optimal
     R = nx.algorithms.flow.edmonds_karp(g, 's', 't')
-    reach, stack = {'s'}, ['s']
+    sink, stack = {'t'}, ['t']
     while stack:
-        u = stack.pop()
-        for v, attr in R[u].items():
-            if v not in reach and attr['capacity'] - attr['flow'] > 0:
-                reach.add(v)
-                stack.append(v)
+        v = stack.pop()
+        for u in R.predecessors(v):
+            if u not in sink and R[u][v]['capacity'] - R[u][v]['flow'] > 0:
+                sink.add(u)
+                stack.append(u)
     out = labels.copy()
     for i in range(n):
-        if i not in reach:
+        if i in sink:
             out[i] = alpha
     return out
 
